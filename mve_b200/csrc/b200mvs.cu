@@ -1,0 +1,1091 @@
+// libb200mvs.so - C ABI of include/b200mvs.h: context, image pyramids, host-side view selection and seeds,
+// frontier (region growing) orchestration and all CUDA kernels.  sm_100a only; no CPU fallback.
+#include "../../include/b200mvs.h"
+#include "patch_opt.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <ctime>
+#include <mutex>
+#include <string>
+#include <vector>
+
+using namespace b200mvs;
+
+// ------------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+std::string g_create_error;
+
+struct HostLevel {
+    int w = 0, h = 0, pitch = 0;
+    float proj[9], invproj[9];
+    uchar4* d_img = nullptr;
+};
+
+struct HostView {
+    bool valid = false;
+    int w = 0, h = 0;
+    float flen = 0, paspect = 1, pp[2] = {0.5f, 0.5f}, rot[9], trans[3];
+    float campos[3];
+    float w2c[12];
+    std::vector<HostLevel> lv;
+    uchar4* d_base = nullptr;      // one allocation for every level
+    size_t bytes = 0;
+};
+
+struct HostFeature {
+    float pos[3];
+    std::vector<int> refs;
+};
+
+struct Entry {                     // frontier queue entry = QueueData (dmrecon.h:28-38)
+    int xy;                        // x | y << 16
+    int jobdir;                    // job | dir << 24 ; -1 = dropped
+    float conf, depth, dzI, dzJ;
+    unsigned slots;
+    int pad;
+};
+static_assert(sizeof(Entry) == 32, "Entry layout");
+
+enum Counter { C_RUN = 0, C_NEXT = 1, C_OVERFLOW = 2, C_SETS = 3, C_OPTS = 4, C_SEED_OK = 5, C_FILLED = 6, C_NUM = 8 };
+
+template <typename T> struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n)
+    {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+} // namespace
+
+struct b200mvs_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::mutex mtx;
+    std::string err;
+    std::vector<HostView> views;
+    std::vector<HostFeature> feats;
+    ViewParams* d_views = nullptr;
+    bool views_dirty = true;
+    float* d_lut = nullptr;
+    // workspace (grown on demand, reused across calls)
+    DevBuf<Entry> ent_a, ent_b, run_in;
+    DevBuf<PatchOut> run_out;
+    DevBuf<unsigned char> written;
+    DevBuf<unsigned long long> counters;
+    DevBuf<JobParams> d_jobs;
+    DevBuf<DevSettings> d_settings;
+    DevBuf<unsigned char> maps;        // all per-job maps of the current batch
+    unsigned long long* h_counters = nullptr;   // pinned
+    std::vector<cudaEvent_t> ev_pool;
+};
+
+namespace {
+
+int fail(b200mvs_ctx* c, int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+    if (c) c->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+    return fail(ctx, B200MVS_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+// ---- reference float arithmetic on the host (libs/math conventions) ----
+inline float dot3(const float* a, const float* b) { return ((0.0f + a[0] * b[0]) + a[1] * b[1]) + a[2] * b[2]; }
+inline float sqn3(const float* a) { return dot3(a, a); }
+inline void normalize3(float* a) { float n = std::sqrt(sqn3(a)); a[0] /= n; a[1] /= n; a[2] /= n; }
+inline float round_mve(float x) { return x > 0.0f ? std::floor(x + 0.5f) : std::ceil(x - 0.5f); }
+inline void world_to_cam(const HostView& v, const float* p, float* o)
+{
+    for (int i = 0; i < 3; ++i) o[i] = dot3(v.w2c + 4 * i, p) + 1.0f * v.w2c[4 * i + 3];
+}
+inline void mat3_mul(const float* m, const float* x, float* o) { for (int i = 0; i < 3; ++i) o[i] = dot3(m + 3 * i, x); }
+
+// CameraInfo::fill_calibration / fill_inverse_calibration (camera.cc:125-144,180-200)
+void fill_calibration(const HostView& v, float ppx, float ppy, float width, float height, float* K, float* Ki)
+{
+    const float dim_aspect = width / height;
+    const float image_aspect = dim_aspect * v.paspect;
+    float ax, ay;
+    if (image_aspect < 1.0f) { ax = v.flen * height / v.paspect; ay = v.flen * height; }
+    else                     { ax = v.flen * width;              ay = v.flen * width * v.paspect; }
+    K[0] = ax;  K[1] = 0.f; K[2] = width * ppx;
+    K[3] = 0.f; K[4] = ay;  K[5] = height * ppy;
+    K[6] = 0.f; K[7] = 0.f; K[8] = 1.f;
+    Ki[0] = 1.0f / ax; Ki[1] = 0.f;       Ki[2] = -width * ppx / ax;
+    Ki[3] = 0.f;       Ki[4] = 1.0f / ay; Ki[5] = -height * ppy / ay;
+    Ki[6] = 0.f;       Ki[7] = 0.f;       Ki[8] = 1.f;
+}
+
+// SingleView::pointInFrustum (single_view.cc:109-121)
+bool point_in_frustum(const HostView& v, const float* wp)
+{
+    float cp[3], sp[3];
+    world_to_cam(v, wp, cp);
+    if (cp[2] <= 0.0f) return false;
+    mat3_mul(v.lv[0].proj, cp, sp);
+    const float x = sp[0] / sp[2] - 0.5f;
+    const float y = sp[1] / sp[2] - 0.5f;
+    return x >= 0 && x <= v.lv[0].w - 1 && y >= 0 && y <= v.lv[0].h - 1;
+}
+inline float foot_print(const HostView& v, int level, const float* p) { float c[3]; world_to_cam(v, p, c); return c[2] * v.lv[level].invproj[0]; }
+
+// mvs_tools.h:46-53
+float parallax(const float* p, const HostView& a, const HostView& b)
+{
+    float d1[3] = {p[0] - a.campos[0], p[1] - a.campos[1], p[2] - a.campos[2]};
+    float d2[3] = {p[0] - b.campos[0], p[1] - b.campos[1], p[2] - b.campos[2]};
+    normalize3(d1); normalize3(d2);
+    const float dp = std::max(std::min(dot3(d1, d2), 1.f), -1.f);
+    return std::acos(dp) * 180.f / 3.141592653589793f;
+}
+
+bool feature_has_view(const HostFeature& f, int id)
+{
+    for (int r : f.refs) if (r == id) return true;
+    return false;
+}
+bool in_aabb(const float* p, const b200mvs_settings& s)
+{
+    for (int i = 0; i < 3; ++i) if (p[i] < s.aabb_min[i] || p[i] > s.aabb_max[i]) return false;
+    return true;
+}
+
+// DMRecon::analyzeFeatures (dmrecon.cc:179-208) + GlobalViewSelection (global_view_selection.cc:17-101).
+// Kept on the host: it is O(views x features) once per reference view and its INTEGER result must match the
+// reference bit for bit, so it uses the reference's float expression order.
+std::vector<int> global_view_selection(const b200mvs_ctx* c, const b200mvs_settings& st, int ref)
+{
+    const int nv = (int)c->views.size();
+    const HostView& rv = c->views[ref];
+    std::vector<std::vector<int>> featInd(nv);
+    for (size_t i = 0; i < c->feats.size(); ++i) {
+        const HostFeature& f = c->feats[i];
+        if (!feature_has_view(f, ref)) continue;
+        if (!point_in_frustum(rv, f.pos)) continue;
+        if (!in_aabb(f.pos, st)) continue;
+        for (int vid : f.refs) {
+            if (vid < 0 || vid >= nv || !c->views[vid].valid) continue;
+            if (point_in_frustum(c->views[vid], f.pos)) featInd[vid].push_back((int)i);
+        }
+    }
+    // SingleView::seesFeature (single_view.h:166-174) as a dense bit table
+    const size_t nf = c->feats.size();
+    std::vector<std::vector<bool>> sees(nv);
+    std::vector<char> avail(nv, 1);
+    avail[ref] = 0;
+    for (int v = 0; v < nv; ++v) if (!c->views[v].valid) avail[v] = 0;
+    std::vector<int> selected;
+    bool found = true;
+    while (found && selected.size() < st.global_vs_max) {
+        float maxBenefit = 0.f;
+        int maxView = 0;
+        found = false;
+        for (int i = 0; i < nv; ++i) {
+            if (!avail[i]) continue;
+            const HostView& tv = c->views[i];
+            float benefit = 0;
+            for (int fid : featInd[i]) {
+                float score = 1.f;
+                const float* fp = c->feats[fid].pos;
+                float plx = parallax(fp, rv, tv);
+                if (plx < st.min_parallax) { const float q = plx / 10.f; score *= q * q; }
+                const float mfp = foot_print(rv, st.scale, fp);
+                const float nfp = foot_print(tv, 0, fp);
+                float ratio = mfp / nfp;
+                if (ratio > 2.) ratio = (float)(2. / ratio);
+                else if (ratio > 1.) ratio = 1.;
+                score *= ratio;
+                for (int sv : selected) {
+                    if (sees[sv].empty()) { sees[sv].assign(nf, false); for (int q : featInd[sv]) sees[sv][q] = true; }
+                    if (!sees[sv][fid]) continue;
+                    plx = parallax(fp, c->views[sv], tv);
+                    if (plx < st.min_parallax) { const float q = plx / 10.f; score *= q * q; }
+                }
+                benefit += score;
+            }
+            if (benefit > maxBenefit) { maxBenefit = benefit; maxView = i; found = true; }
+        }
+        if (found) {
+            selected.insert(std::upper_bound(selected.begin(), selected.end(), maxView), maxView);
+            avail[maxView] = 0;
+        }
+    }
+    return selected;
+}
+
+struct Seed { int x, y; float depth; };
+
+// The feature loop of DMRecon::processFeatures (dmrecon.cc:258-292): which features seed, at which pixel, with
+// which initial depth.  The optimisation of the seeds runs on the device.
+std::vector<Seed> collect_seeds(const b200mvs_ctx* c, const b200mvs_settings& st, int ref, const std::vector<int>& gsel)
+{
+    const HostView& rv = c->views[ref];
+    std::vector<Seed> out;
+    for (const HostFeature& f : c->feats) {
+        bool use = feature_has_view(f, ref);
+        for (size_t k = 0; !use && k < gsel.size(); ++k) if (feature_has_view(f, gsel[k])) use = true;
+        if (!use) continue;
+        if (!point_in_frustum(rv, f.pos)) continue;
+        if (!in_aabb(f.pos, st)) continue;
+        float cp[3], sp[3];
+        world_to_cam(rv, f.pos, cp);
+        mat3_mul(rv.lv[st.scale].proj, cp, sp);
+        const float px = sp[0] / sp[2] - 0.5f, py = sp[1] / sp[2] - 0.5f;
+        const float dv[3] = {f.pos[0] - rv.campos[0], f.pos[1] - rv.campos[1], f.pos[2] - rv.campos[2]};
+        Seed s;
+        s.x = (int)round_mve(px);
+        s.y = (int)round_mve(py);
+        s.depth = std::sqrt(sqn3(dv));
+        out.push_back(s);
+    }
+    return out;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernels: image import + pyramid
+// ------------------------------------------------------------------------------------------------
+// `undistorted` bytes -> RGBX8 (alpha dropped, grey expanded: image_pyramid.cc:65-73)
+__global__ void k_import_rgb(const uint8_t* __restrict__ src, int w, int h, int ch, uchar4* __restrict__ dst, int pitch)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    const uint8_t* p = src + ((size_t)y * w + x) * ch;
+    uchar4 o;
+    if (ch >= 3) { o.x = p[0]; o.y = p[1]; o.z = p[2]; }
+    else         { o.x = o.y = o.z = p[0]; }
+    o.w = 255;
+    dst[(size_t)y * pitch + x] = o;
+}
+
+// mve::image::rescale_half_size_gaussian<uint8_t>(img, 1.f) (image_tools.h:617-694) with Accum<uint8>
+// (accum.h:117-170): same 16 taps in the same order, fp32 accumulate, true division, math::round.
+// Bit-exact with the reference (tests/test_pyramid.py); products and sums are kept un-fused on purpose.
+__global__ void k_half_gaussian(const uchar4* __restrict__ in, int iw, int ih, int ipitch,
+                                uchar4* __restrict__ out, int ow, int oh, int opitch,
+                                float w1, float w2, float w3)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= ow || y >= oh) return;
+    const int y2 = y * 2, x2 = x * 2;
+    const int ys[4] = {max(0, y2 - 1), y2, min(ih - 1, y2 + 1), min(ih - 1, y2 + 2)};
+    const int xs[4] = {max(0, x2 - 1), x2, min(iw - 1, x2 + 1), min(iw - 1, x2 + 2)};
+    const float wr[4][4] = {{w3, w2, w2, w3}, {w2, w1, w1, w2}, {w2, w1, w1, w2}, {w3, w2, w2, w3}};
+    float v0 = 0.f, v1 = 0.f, v2 = 0.f, ws = 0.f;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const uchar4* row = in + (size_t)ys[r] * ipitch;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uchar4 t = row[xs[k]];
+            v0 = __fadd_rn(v0, __fmul_rn((float)t.x, wr[r][k]));
+            v1 = __fadd_rn(v1, __fmul_rn((float)t.y, wr[r][k]));
+            v2 = __fadd_rn(v2, __fmul_rn((float)t.z, wr[r][k]));
+            ws = __fadd_rn(ws, wr[r][k]);
+        }
+    }
+    const float q0 = __fdiv_rn(v0, ws), q1 = __fdiv_rn(v1, ws), q2 = __fdiv_rn(v2, ws);
+    uchar4 o;
+    o.x = (unsigned char)(q0 > 0.f ? floorf(q0 + 0.5f) : ceilf(q0 - 0.5f));
+    o.y = (unsigned char)(q1 > 0.f ? floorf(q1 + 0.5f) : ceilf(q1 - 0.5f));
+    o.z = (unsigned char)(q2 > 0.f ? floorf(q2 + 0.5f) : ceilf(q2 - 0.5f));
+    o.w = 255;
+    out[(size_t)y * opitch + x] = o;
+}
+
+__global__ void k_export_rgb(const uchar4* __restrict__ src, int w, int h, int pitch, uint8_t* __restrict__ dst)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    const uchar4 t = src[(size_t)y * pitch + x];
+    uint8_t* p = dst + ((size_t)y * w + x) * 3;
+    p[0] = t.x; p[1] = t.y; p[2] = t.z;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernels: patch optimisation + frontier
+// ------------------------------------------------------------------------------------------------
+constexpr int OPT_WARPS = 4;
+
+// One warp per queue entry: PatchOptimization ctor + doAutoOptimization + computeConfidence.
+__global__ void __launch_bounds__(OPT_WARPS * 32)
+k_optimize(const Entry* __restrict__ in, PatchOut* __restrict__ out, const unsigned long long* __restrict__ n_ptr, int n_max,
+           const DevSettings* __restrict__ st, const JobParams* __restrict__ jobs, const ViewParams* __restrict__ views,
+           const float* __restrict__ g_lut, unsigned long long* __restrict__ counters)
+{
+    __shared__ float lut[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = g_lut[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int wid = blockIdx.x * OPT_WARPS + (threadIdx.x >> 5);
+    const int n = n_ptr ? (int)min((unsigned long long)n_max, *n_ptr) : n_max;
+    if (wid >= n) return;
+    const Entry e = in[wid];
+    PatchIn pi;
+    pi.x = e.xy & 0xFFFF; pi.y = (e.xy >> 16) & 0xFFFF;
+    pi.depth = e.depth; pi.dzI = e.dzI; pi.dzJ = e.dzJ; pi.slots = e.slots;
+    const JobParams* job = &jobs[e.jobdir & 0xFFFFFF];
+    PatchOut po;
+    const unsigned sets = optimize_patch(st, job, views, lut, lane, pi, po);
+    if (lane == 0) {
+        out[wid] = po;
+        atomicAdd(&counters[C_SETS], (unsigned long long)sets);
+        atomicAdd(&counters[C_OPTS], 1ull);
+    }
+}
+
+__device__ __forceinline__ unsigned long long entry_key(const Entry& e)
+{
+    // larger confidence first, then smaller direction code (DESIGN.md "Frontier schedule")
+    return ((unsigned long long)__float_as_uint(e.conf) << 8) | (unsigned long long)(7 - ((e.jobdir >> 24) & 7));
+}
+
+// Round step A+C (first half): stale test (dmrecon.cc:371) and per-pixel bid.
+__global__ void k_select(Entry* __restrict__ cur, int n, const JobParams* __restrict__ jobs)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Entry e = cur[i];
+    const JobParams& J = jobs[e.jobdir & 0xFFFFFF];
+    const int idx = ((e.xy >> 16) & 0xFFFF) * J.W + (e.xy & 0xFFFF);
+    if (J.conf[idx] > e.conf) { cur[i].jobdir = -1; return; }
+    atomicMax(&J.sel[idx], entry_key(e));
+}
+
+// Round step C (second half): the winning bid of each pixel runs, the others are carried to the next round.
+__global__ void k_pick(const Entry* __restrict__ cur, int n, const JobParams* __restrict__ jobs,
+                       Entry* __restrict__ run, Entry* __restrict__ next, unsigned long long cap,
+                       unsigned long long* __restrict__ counters)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Entry e = cur[i];
+    if (e.jobdir == -1) return;
+    const JobParams& J = jobs[e.jobdir & 0xFFFFFF];
+    const int idx = ((e.xy >> 16) & 0xFFFF) * J.W + (e.xy & 0xFFFF);
+    const unsigned long long key = entry_key(e);
+    if (J.sel[idx] == key && atomicCAS(&J.sel[idx], key, 0ull) == key) {
+        const unsigned long long pos = atomicAdd(&counters[C_RUN], 1ull);
+        run[pos] = e;                       // |run| <= n <= capacity
+    } else {
+        const unsigned long long pos = atomicAdd(&counters[C_NEXT], 1ull);
+        if (pos < cap) next[pos] = e; else counters[C_OVERFLOW] = 1ull;
+    }
+}
+
+// Round step D: commit (dmrecon.cc:377-398).  One winner per pixel, so plain stores.
+__global__ void k_commit(const Entry* __restrict__ run, const PatchOut* __restrict__ res, const unsigned long long* __restrict__ n_ptr,
+                         const JobParams* __restrict__ jobs, unsigned char* __restrict__ written,
+                         unsigned long long* __restrict__ counters, unsigned long long* __restrict__ filled)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int)*n_ptr) return;
+    const Entry e = run[i];
+    const PatchOut r = res[i];
+    const int j = e.jobdir & 0xFFFFFF;
+    const JobParams& J = jobs[j];
+    const int idx = ((e.xy >> 16) & 0xFFFF) * J.W + (e.xy & 0xFFFF);
+    unsigned char w = 0;
+    if (!(r.conf == 0.f)) {
+        const float old = J.conf[idx];
+        if (old <= 0.f) atomicAdd(&filled[j], 1ull);
+        if (old < r.conf) {
+            J.depth[idx] = r.depth;
+            J.conf[idx] = r.conf;
+            J.dz[2 * idx] = r.dzI; J.dz[2 * idx + 1] = r.dzJ;
+            J.normal[3 * idx] = r.nx; J.normal[3 * idx + 1] = r.ny; J.normal[3 * idx + 2] = r.nz;
+            J.slots[idx] = r.slots;
+            w = 1;
+        }
+    }
+    written[i] = w;
+}
+
+// Round step E: push the 4-neighbours of every committed pixel (dmrecon.cc:400-431).
+__global__ void k_expand(const Entry* __restrict__ run, const PatchOut* __restrict__ res, const unsigned char* __restrict__ written,
+                         const unsigned long long* __restrict__ n_ptr, const JobParams* __restrict__ jobs,
+                         Entry* __restrict__ next, unsigned long long cap, unsigned long long* __restrict__ counters)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int)*n_ptr) return;
+    if (!written[i]) return;
+    const Entry e = run[i];
+    const PatchOut r = res[i];
+    const int j = e.jobdir & 0xFFFFFF;
+    const JobParams& J = jobs[j];
+    const int x = e.xy & 0xFFFF, y = (e.xy >> 16) & 0xFFFF;
+    const int nx[4] = {x - 1, x + 1, x, x};
+    const int ny[4] = {y, y, y - 1, y + 1};
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+        const float c = J.conf[ny[d] * J.W + nx[d]];
+        if (c < r.conf - 0.05f || c == 0.f) {
+            Entry o;
+            o.xy = nx[d] | (ny[d] << 16);
+            o.jobdir = j | (d << 24);
+            o.conf = r.conf; o.depth = r.depth; o.dzI = r.dzI; o.dzJ = r.dzJ; o.slots = r.slots; o.pad = 0;
+            const unsigned long long pos = atomicAdd(&counters[C_NEXT], 1ull);
+            if (pos < cap) next[pos] = o; else counters[C_OVERFLOW] = 1ull;
+        }
+    }
+}
+
+// Seeds (dmrecon.cc:296-326): per pixel the most confident seed, first in feature order on ties.
+__global__ void k_seed_select(const Entry* __restrict__ seeds, const PatchOut* __restrict__ res, int n,
+                              const JobParams* __restrict__ jobs, unsigned long long* __restrict__ counters)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const PatchOut r = res[i];
+    if (!(r.conf > 0.f)) return;
+    atomicAdd(&counters[C_SEED_OK], 1ull);
+    const Entry e = seeds[i];
+    const JobParams& J = jobs[e.jobdir & 0xFFFFFF];
+    const int idx = ((e.xy >> 16) & 0xFFFF) * J.W + (e.xy & 0xFFFF);
+    atomicMax(&J.sel[idx], ((unsigned long long)__float_as_uint(r.conf) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i));
+}
+__global__ void k_seed_commit(const Entry* __restrict__ seeds, const PatchOut* __restrict__ res, int n,
+                              const JobParams* __restrict__ jobs, Entry* __restrict__ next, unsigned long long cap,
+                              unsigned long long* __restrict__ counters, unsigned long long* __restrict__ filled)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const PatchOut r = res[i];
+    if (!(r.conf > 0.f)) return;
+    const Entry e = seeds[i];
+    const int j = e.jobdir & 0xFFFFFF;
+    const JobParams& J = jobs[j];
+    const int idx = ((e.xy >> 16) & 0xFFFF) * J.W + (e.xy & 0xFFFF);
+    const unsigned long long key = ((unsigned long long)__float_as_uint(r.conf) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i);
+    if (J.sel[idx] != key) return;
+    J.sel[idx] = 0ull;
+    atomicAdd(&filled[j], 1ull);
+    J.depth[idx] = r.depth;
+    J.conf[idx] = r.conf;
+    J.dz[2 * idx] = r.dzI; J.dz[2 * idx + 1] = r.dzJ;
+    J.normal[3 * idx] = r.nx; J.normal[3 * idx + 1] = r.ny; J.normal[3 * idx + 2] = r.nz;
+    J.slots[idx] = r.slots;
+    Entry o;
+    o.xy = e.xy; o.jobdir = j | (4 << 24);
+    o.conf = r.conf; o.depth = r.depth; o.dzI = r.dzI; o.dzJ = r.dzJ; o.slots = r.slots; o.pad = 0;
+    const unsigned long long pos = atomicAdd(&counters[C_NEXT], 1ull);
+    if (pos < cap) next[pos] = o; else counters[C_OVERFLOW] = 1ull;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host: view upload
+// ------------------------------------------------------------------------------------------------
+int check_settings(b200mvs_ctx* ctx, const b200mvs_settings* s)
+{
+    if (!s) return fail(ctx, B200MVS_ERR_INVALID_ARG, "settings is NULL");
+    if (s->filter_width != 5)
+        return fail(ctx, B200MVS_ERR_UNSUPPORTED, "filterWidth must be 5 (the reference hard-codes patchPoints[12], patch_sampler.cc:96)");
+    if (s->scale < 0) return fail(ctx, B200MVS_ERR_INVALID_ARG, "Invalid scale factor");
+    if (s->nr_recon_neighbors < 1 || s->nr_recon_neighbors > B200MVS_MAX_LOCAL_VIEWS)
+        return fail(ctx, B200MVS_ERR_UNSUPPORTED, "nrReconNeighbors must be in 1..%d", B200MVS_MAX_LOCAL_VIEWS);
+    if (s->global_vs_max < 1 || s->global_vs_max > B200MVS_MAX_GLOBAL_VIEWS)
+        return fail(ctx, B200MVS_ERR_UNSUPPORTED, "globalVSMax must be in 1..%d", B200MVS_MAX_GLOBAL_VIEWS);
+    if (s->frontier_band > 0.f)
+        return fail(ctx, B200MVS_ERR_UNSUPPORTED, "frontier_band > 0 is reserved");
+    return 0;
+}
+
+DevSettings to_dev(const b200mvs_settings& s)
+{
+    DevSettings d;
+    d.min_ncc = s.min_ncc; d.min_parallax = s.min_parallax; d.accept_ncc = s.accept_ncc; d.min_refine_diff = s.min_refine_diff;
+    d.max_iterations = s.max_iterations; d.nr_recon_neighbors = s.nr_recon_neighbors;
+    d.scale = s.scale; d.use_color_scale = s.use_color_scale;
+    return d;
+}
+
+int upload_common(b200mvs_ctx* ctx, int id, const uint8_t* d_src, int w, int h, int ch, float flen, float paspect,
+                  const float* pp, const float* rot, const float* trans, cudaStream_t stream)
+{
+    HostView& v = ctx->views[id];
+    if (v.d_base) { cudaFree(v.d_base); v.d_base = nullptr; }
+    v.valid = false;
+    v.w = w; v.h = h; v.flen = flen; v.paspect = paspect; v.pp[0] = pp[0]; v.pp[1] = pp[1];
+    std::memcpy(v.rot, rot, sizeof(v.rot));
+    std::memcpy(v.trans, trans, sizeof(v.trans));
+    // CameraInfo::fill_camera_pos / fill_world_to_cam (camera.cc:34-39,61-67)
+    v.campos[0] = -rot[0] * trans[0] - rot[3] * trans[1] - rot[6] * trans[2];
+    v.campos[1] = -rot[1] * trans[0] - rot[4] * trans[1] - rot[7] * trans[2];
+    v.campos[2] = -rot[2] * trans[0] - rot[5] * trans[1] - rot[8] * trans[2];
+    for (int r = 0; r < 3; ++r) {
+        v.w2c[4 * r] = rot[3 * r]; v.w2c[4 * r + 1] = rot[3 * r + 1]; v.w2c[4 * r + 2] = rot[3 * r + 2]; v.w2c[4 * r + 3] = trans[r];
+    }
+    // buildPyramid (image_pyramid.cc:22-53)
+    v.lv.clear();
+    float ppx = pp[0], ppy = pp[1];
+    int cw = w, chh = h;
+    auto push_level = [&]() {
+        HostLevel L; L.w = cw; L.h = chh; L.pitch = (cw + 3) & ~3;
+        fill_calibration(v, ppx, ppy, (float)cw, (float)chh, L.proj, L.invproj);
+        v.lv.push_back(L);
+    };
+    push_level();
+    while (std::min(cw, chh) >= 30) {
+        if (cw % 2 == 1) ppx = ppx * float(cw) / float(cw + 1);
+        if (chh % 2 == 1) ppy = ppy * float(chh) / float(chh + 1);
+        cw = (cw + 1) / 2; chh = (chh + 1) / 2;
+        push_level();
+    }
+    if ((int)v.lv.size() > MAX_LEVELS) return fail(ctx, B200MVS_ERR_UNSUPPORTED, "image too large: %d pyramid levels", (int)v.lv.size());
+    size_t total = 0;
+    for (HostLevel& L : v.lv) total += (size_t)L.pitch * L.h;
+    CK(cudaMalloc(&v.d_base, total * sizeof(uchar4)));
+    v.bytes = total * sizeof(uchar4);
+    size_t off = 0;
+    for (HostLevel& L : v.lv) { L.d_img = v.d_base + off; off += (size_t)L.pitch * L.h; }
+    const dim3 blk(32, 8);
+    k_import_rgb<<<dim3((w + 31) / 32, (h + 7) / 8), blk, 0, stream>>>(d_src, w, h, ch, v.lv[0].d_img, v.lv[0].pitch);
+    // ensureImages (image_pyramid.cc:56-95): rescale_half_size_gaussian(img, 1.f) level by level
+    const float w1 = std::exp(-0.5f / (2.0f * 1.0f)), w2 = std::exp(-2.5f / (2.0f * 1.0f)), w3 = std::exp(-4.5f / (2.0f * 1.0f));
+    for (size_t i = 1; i < v.lv.size(); ++i) {
+        const HostLevel& a = v.lv[i - 1];
+        const HostLevel& b = v.lv[i];
+        k_half_gaussian<<<dim3((b.w + 31) / 32, (b.h + 7) / 8), blk, 0, stream>>>(a.d_img, a.w, a.h, a.pitch, b.d_img, b.w, b.h, b.pitch, w1, w2, w3);
+    }
+    CK(cudaGetLastError());
+    v.valid = true;
+    ctx->views_dirty = true;
+    return 0;
+}
+
+int sync_view_params(b200mvs_ctx* ctx)
+{
+    if (!ctx->views_dirty) return 0;
+    std::vector<ViewParams> hp(ctx->views.size());
+    std::memset(hp.data(), 0, hp.size() * sizeof(ViewParams));
+    for (size_t i = 0; i < ctx->views.size(); ++i) {
+        const HostView& v = ctx->views[i];
+        ViewParams& p = hp[i];
+        p.valid = v.valid ? 1 : 0;
+        if (!v.valid) continue;
+        std::memcpy(p.campos, v.campos, 12);
+        std::memcpy(p.w2c, v.w2c, 48);
+        std::memcpy(p.rot, v.rot, 36);
+        p.inv_ax0 = v.lv[0].invproj[0];
+        p.nlevels = (int)v.lv.size();
+        for (size_t l = 0; l < v.lv.size(); ++l) {
+            const HostLevel& L = v.lv[l];
+            p.lv[l].ax = L.proj[0]; p.lv[l].ay = L.proj[4]; p.lv[l].cx = L.proj[2]; p.lv[l].cy = L.proj[5];
+            p.lv[l].w = L.w; p.lv[l].h = L.h; p.lv[l].pitch = L.pitch; p.lv[l].img = L.d_img;
+        }
+    }
+    CK(cudaMemcpyAsync(ctx->d_views, hp.data(), hp.size() * sizeof(ViewParams), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->views_dirty = false;
+    return 0;
+}
+
+cudaEvent_t get_event(b200mvs_ctx* ctx, size_t i)
+{
+    while (ctx->ev_pool.size() <= i) { cudaEvent_t e; cudaEventCreate(&e); ctx->ev_pool.push_back(e); }
+    return ctx->ev_pool[i];
+}
+
+// JobParams of one reference view (everything except the map pointers)
+int make_job(b200mvs_ctx* ctx, const b200mvs_settings& s, int ref, const std::vector<int>& gsel, JobParams& J)
+{
+    const HostView& rv = ctx->views[ref];
+    if (s.scale >= (int)rv.lv.size()) return fail(ctx, B200MVS_ERR_INVALID_ARG, "Invalid scale factor");
+    const HostLevel& L = rv.lv[s.scale];
+    std::memset(&J, 0, sizeof(J));
+    J.ref_view = ref; J.W = L.w; J.H = L.h; J.n_global = (int)gsel.size();
+    for (size_t k = 0; k < gsel.size(); ++k) J.gview[k] = gsel[k];
+    J.ki0 = L.invproj[0]; J.ki2 = L.invproj[2]; J.ki4 = L.invproj[4]; J.ki5 = L.invproj[5];
+    J.ref_img = L.d_img; J.ref_pitch = L.pitch;
+    return 0;
+}
+
+unsigned ids_to_slots(const std::vector<int>& gsel, const int32_t* ids, int n, bool* ok)
+{
+    unsigned s = 0xFFFFFFFFu;
+    std::vector<int> slots;
+    for (int k = 0; k < n; ++k) {
+        auto it = std::lower_bound(gsel.begin(), gsel.end(), (int)ids[k]);
+        if (it == gsel.end() || *it != ids[k]) { *ok = false; return s; }
+        slots.push_back((int)(it - gsel.begin()));
+    }
+    std::sort(slots.begin(), slots.end());
+    for (size_t k = 0; k < slots.size() && k < 4; ++k) s = (s & ~(0xFFu << (8 * k))) | ((unsigned)slots[k] << (8 * k));
+    *ok = true;
+    return s;
+}
+
+} // namespace
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* b200mvs_version(void) { return "b200mvs 0.1 (sm_100a)"; }
+
+void b200mvs_default_settings(b200mvs_settings* s)
+{
+    if (!s) return;
+    s->filter_width = 5; s->min_ncc = 0.3f; s->min_parallax = 10.0f; s->accept_ncc = 0.6f; s->min_refine_diff = 0.001f;
+    s->max_iterations = 20; s->nr_recon_neighbors = 4; s->global_vs_max = 20; s->scale = 0; s->use_color_scale = 1;
+    for (int i = 0; i < 3; ++i) { s->aabb_min[i] = -3.402823466e+38f; s->aabb_max[i] = 3.402823466e+38f; }
+    s->frontier_band = 0.f;
+}
+
+const char* b200mvs_last_error(const b200mvs_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int b200mvs_create(int device, int n_views, b200mvs_ctx** out)
+{
+    b200mvs_ctx* ctx = nullptr;
+    if (!out || n_views <= 0) return fail(nullptr, B200MVS_ERR_INVALID_ARG, "b200mvs_create: bad arguments");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, B200MVS_ERR_CUDA, "no CUDA device available (%s); b200mvs has no CPU fallback", cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(nullptr, B200MVS_ERR_INVALID_ARG, "device %d out of range (%d devices)", device, ndev);
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return fail(nullptr, B200MVS_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    ctx = new b200mvs_ctx();
+    ctx->device = device;
+    ctx->views.resize(n_views);
+    auto bail = [&](const char* what, cudaError_t ce) {
+        fail(nullptr, B200MVS_ERR_CUDA, "%s: %s", what, cudaGetErrorString(ce));
+        delete ctx;
+        return B200MVS_ERR_CUDA;
+    };
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    if ((e = cudaMalloc(&ctx->d_views, sizeof(ViewParams) * n_views)) != cudaSuccess) return bail("cudaMalloc(views)", e);
+    if ((e = cudaMalloc(&ctx->d_lut, 256 * sizeof(float))) != cudaSuccess) return bail("cudaMalloc(lut)", e);
+    if ((e = cudaMallocHost(&ctx->h_counters, sizeof(unsigned long long) * 4096)) != cudaSuccess) return bail("cudaMallocHost", e);
+    // sRGB code value -> linear: the formula documented at mvs_tools.cc:21-29; tests/test_lut.py checks the
+    // 256 floats against the reference table.
+    float lut[256];
+    for (int i = 0; i < 256; ++i) {
+        const double x = i / 255.0;
+        lut[i] = (float)((i <= 0.04045 * 255.0) ? x / 12.92 : std::pow((x + 0.055) / 1.055, 2.4));
+    }
+    if ((e = cudaMemcpy(ctx->d_lut, lut, sizeof(lut), cudaMemcpyHostToDevice)) != cudaSuccess) return bail("cudaMemcpy(lut)", e);
+    *out = ctx;
+    return 0;
+}
+
+void b200mvs_destroy(b200mvs_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    for (HostView& v : ctx->views) if (v.d_base) cudaFree(v.d_base);
+    if (ctx->d_views) cudaFree(ctx->d_views);
+    if (ctx->d_lut) cudaFree(ctx->d_lut);
+    if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+    ctx->ent_a.release(); ctx->ent_b.release(); ctx->run_in.release(); ctx->run_out.release(); ctx->written.release();
+    ctx->counters.release(); ctx->d_jobs.release(); ctx->d_settings.release(); ctx->maps.release();
+    for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int b200mvs_upload_view(b200mvs_ctx* ctx, int id, const uint8_t* rgb, int w, int h, int channels,
+                        float flen, float paspect, const float ppoint[2], const float rot[9], const float trans[3])
+{
+    if (!ctx) return B200MVS_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mtx);
+    if (id < 0 || id >= (int)ctx->views.size() || !rgb || w < 2 || h < 2 || !ppoint || !rot || !trans)
+        return fail(ctx, B200MVS_ERR_INVALID_ARG, "b200mvs_upload_view: bad arguments");
+    if (channels < 1 || channels > 4) return fail(ctx, B200MVS_ERR_INVALID_ARG, "Image with invalid number of channels");
+    CK(cudaSetDevice(ctx->device));
+    uint8_t* d_src = nullptr;
+    const size_t bytes = (size_t)w * h * channels;
+    CK(cudaMalloc(&d_src, bytes));
+    cudaError_t e = cudaMemcpyAsync(d_src, rgb, bytes, cudaMemcpyHostToDevice, ctx->stream);
+    int rc = 0;
+    if (e != cudaSuccess) rc = fail(ctx, B200MVS_ERR_CUDA, "cudaMemcpyAsync: %s", cudaGetErrorString(e));
+    if (!rc) rc = upload_common(ctx, id, d_src, w, h, channels, flen, paspect, ppoint, rot, trans, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_src);
+    return rc;
+}
+
+int b200mvs_upload_view_device(b200mvs_ctx* ctx, int id, const uint8_t* rgb_dev, int w, int h,
+                               float flen, float paspect, const float ppoint[2], const float rot[9], const float trans[3],
+                               void* cuda_stream)
+{
+    if (!ctx) return B200MVS_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mtx);
+    if (id < 0 || id >= (int)ctx->views.size() || !rgb_dev || w < 2 || h < 2 || !ppoint || !rot || !trans)
+        return fail(ctx, B200MVS_ERR_INVALID_ARG, "b200mvs_upload_view_device: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    int rc = upload_common(ctx, id, rgb_dev, w, h, 3, flen, paspect, ppoint, rot, trans, s);
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (!rc && e != cudaSuccess) rc = fail(ctx, B200MVS_ERR_CUDA, "upload sync: %s", cudaGetErrorString(e));
+    return rc;
+}
+
+int b200mvs_set_features(b200mvs_ctx* ctx, int n, const float* pos, const int32_t* off, const int32_t* ids)
+{
+    if (!ctx) return B200MVS_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mtx);
+    if (n < 0 || (n > 0 && (!pos || !off || !ids))) return fail(ctx, B200MVS_ERR_INVALID_ARG, "b200mvs_set_features: bad arguments");
+    ctx->feats.resize(n);
+    for (int i = 0; i < n; ++i) {
+        std::memcpy(ctx->feats[i].pos, pos + 3 * i, 12);
+        ctx->feats[i].refs.assign(ids + off[i], ids + off[i + 1]);
+    }
+    return 0;
+}
+
+int b200mvs_num_levels(b200mvs_ctx* ctx, int id)
+{
+    if (!ctx || id < 0 || id >= (int)ctx->views.size() || !ctx->views[id].valid) return B200MVS_ERR_INVALID_ARG;
+    return (int)ctx->views[id].lv.size();
+}
+
+int b200mvs_get_level(b200mvs_ctx* ctx, int id, int level, int* w, int* h, uint8_t* rgb)
+{
+    if (!ctx) return B200MVS_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mtx);
+    if (id < 0 || id >= (int)ctx->views.size() || !ctx->views[id].valid) return fail(ctx, B200MVS_ERR_INVALID_ARG, "invalid view");
+    const HostView& v = ctx->views[id];
+    if (level < 0 || level >= (int)v.lv.size()) return fail(ctx, B200MVS_ERR_INVALID_ARG, "invalid level");
+    const HostLevel& L = v.lv[level];
+    if (w) *w = L.w;
+    if (h) *h = L.h;
+    if (!rgb) return 0;
+    CK(cudaSetDevice(ctx->device));
+    uint8_t* d = nullptr;
+    CK(cudaMalloc(&d, (size_t)L.w * L.h * 3));
+    k_export_rgb<<<dim3((L.w + 31) / 32, (L.h + 7) / 8), dim3(32, 8), 0, ctx->stream>>>(L.d_img, L.w, L.h, L.pitch, d);
+    cudaError_t e = cudaMemcpyAsync(rgb, d, (size_t)L.w * L.h * 3, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(ctx, B200MVS_ERR_CUDA, "get_level copy: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+int b200mvs_global_view_selection(b200mvs_ctx* ctx, const b200mvs_settings* s, int ref, int32_t* ids_out, int cap)
+{
+    if (!ctx) return B200MVS_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mtx);
+    int rc = check_settings(ctx, s);
+    if (rc) return rc;
+    if (ref < 0 || ref >= (int)ctx->views.size()) return fail(ctx, B200MVS_ERR_INVALID_ARG, "Master view index out of bounds");
+    if (!ctx->views[ref].valid) return fail(ctx, B200MVS_ERR_INVALID_ARG, "Invalid master view");
+    if (s->scale >= (int)ctx->views[ref].lv.size()) return fail(ctx, B200MVS_ERR_INVALID_ARG, "Invalid scale factor");
+    std::vector<int> sel = global_view_selection(ctx, *s, ref);
+    for (int i = 0; i < (int)sel.size() && i < cap; ++i) ids_out[i] = sel[i];
+    return (int)sel.size();
+}
+
+int b200mvs_optimize_patches(b200mvs_ctx* ctx, const b200mvs_settings* s, int ref, const int32_t* gids, int ng,
+                             const b200mvs_patch_in* in, int n, b200mvs_patch_out* out, b200mvs_stats* stats)
+{
+    if (!ctx) return B200MVS_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mtx);
+    int rc = check_settings(ctx, s);
+    if (rc) return rc;
+    if (ref < 0 || ref >= (int)ctx->views.size()) return fail(ctx, B200MVS_ERR_INVALID_ARG, "Master view index out of bounds");
+    if (!ctx->views[ref].valid) return fail(ctx, B200MVS_ERR_INVALID_ARG, "Invalid master view");
+    if (ng < 1 || ng > MAX_GLOBAL || !gids || n < 0 || (n > 0 && (!in || !out)))
+        return fail(ctx, B200MVS_ERR_INVALID_ARG, "b200mvs_optimize_patches: bad arguments");
+    std::vector<int> gsel(gids, gids + ng);
+    if (!std::is_sorted(gsel.begin(), gsel.end())) return fail(ctx, B200MVS_ERR_INVALID_ARG, "global ids must be ascending");
+    for (int g : gsel) if (g < 0 || g >= (int)ctx->views.size() || !ctx->views[g].valid) return fail(ctx, B200MVS_ERR_INVALID_ARG, "invalid global view id");
+    if (stats) std::memset(stats, 0, sizeof(*stats));
+    if (n == 0) return 0;
+    CK(cudaSetDevice(ctx->device));
+    if ((rc = sync_view_params(ctx))) return rc;
+    JobParams J;
+    if ((rc = make_job(ctx, *s, ref, gsel, J))) return rc;
+    std::vector<Entry> he(n);
+    for (int i = 0; i < n; ++i) {
+        bool ok = true;
+        if (in[i].n_local < 0 || in[i].n_local > 4) return fail(ctx, B200MVS_ERR_INVALID_ARG, "patch %d: n_local out of range", i);
+        if (in[i].x < 0 || in[i].y < 0 || in[i].x > 0xFFFF || in[i].y > 0xFFFF) { he[i].xy = 0xFFFF | (0xFFFF << 16); }
+        else he[i].xy = in[i].x | (in[i].y << 16);
+        he[i].jobdir = 0;
+        he[i].conf = 0.f; he[i].depth = in[i].depth; he[i].dzI = in[i].dz_i; he[i].dzJ = in[i].dz_j;
+        he[i].slots = ids_to_slots(gsel, in[i].local_ids, in[i].n_local, &ok);
+        he[i].pad = 0;
+        if (!ok) return fail(ctx, B200MVS_ERR_INVALID_ARG, "patch %d: local view id not in the global set", i);
+    }
+    CK(ctx->run_in.reserve(n));
+    CK(ctx->run_out.reserve(n));
+    CK(ctx->counters.reserve(C_NUM + 8));
+    CK(ctx->d_jobs.reserve(1));
+    CK(ctx->d_settings.reserve(1));
+    const DevSettings ds = to_dev(*s);
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemcpyAsync(ctx->run_in.p, he.data(), sizeof(Entry) * n, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_jobs.p, &J, sizeof(J), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_settings.p, &ds, sizeof(ds), cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(ctx->counters.p, 0, sizeof(unsigned long long) * C_NUM, st));
+    cudaEvent_t e0 = get_event(ctx, 0), e1 = get_event(ctx, 1);
+    CK(cudaEventRecord(e0, st));
+    k_optimize<<<(n + OPT_WARPS - 1) / OPT_WARPS, OPT_WARPS * 32, 0, st>>>(ctx->run_in.p, ctx->run_out.p, nullptr, n, ctx->d_settings.p,
+                                                                         ctx->d_jobs.p, ctx->d_views, ctx->d_lut, ctx->counters.p);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(e1, st));
+    std::vector<PatchOut> ho(n);
+    CK(cudaMemcpyAsync(ho.data(), ctx->run_out.p, sizeof(PatchOut) * n, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(ctx->h_counters, ctx->counters.p, sizeof(unsigned long long) * C_NUM, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (int i = 0; i < n; ++i) {
+        const PatchOut& r = ho[i];
+        b200mvs_patch_out& o = out[i];
+        o.conf = r.conf; o.depth = r.depth; o.dz_i = r.dzI; o.dz_j = r.dzJ;
+        o.normal[0] = r.nx; o.normal[1] = r.ny; o.normal[2] = r.nz;
+        o.n_local = 0;
+        for (int k = 0; k < 4; ++k) {
+            const int sl = (r.slots >> (8 * k)) & 0xFF;
+            o.local_ids[k] = (sl != 0xFF && sl < ng) ? gsel[sl] : -1;
+            if (o.local_ids[k] >= 0) o.n_local++;
+        }
+        o.iterations = r.iterations; o.converged = r.flags & 1; o.opti_success = (r.flags >> 1) & 1;
+    }
+    if (stats) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        stats->n_opt = ctx->h_counters[C_OPTS];
+        stats->n_sample_sets = ctx->h_counters[C_SETS];
+        stats->ms_patch_kernel = ms; stats->ms_total_device = ms;
+        stats->n_patch_launches = 1; stats->n_kernel_launches = 1;
+    }
+    return 0;
+}
+
+int b200mvs_reconstruct(b200mvs_ctx* ctx, const b200mvs_settings* s, int n_refs, const int32_t* refs,
+                        b200mvs_maps* maps, b200mvs_progress* progress, b200mvs_stats* stats, int32_t* failed_view)
+{
+    if (!ctx) return B200MVS_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mtx);
+    int rc = check_settings(ctx, s);
+    if (rc) return rc;
+    if (n_refs < 1 || !refs || n_refs > 4000) return fail(ctx, B200MVS_ERR_INVALID_ARG, "b200mvs_reconstruct: bad arguments");
+    if (failed_view) *failed_view = -1;
+    if (stats) std::memset(stats, 0, sizeof(*stats));
+    for (int j = 0; j < n_refs; ++j) {
+        const int r = refs[j];
+        if (failed_view) *failed_view = r;
+        if (r < 0 || r >= (int)ctx->views.size()) return fail(ctx, B200MVS_ERR_INVALID_ARG, "Master view index out of bounds");
+        if (!ctx->views[r].valid) return fail(ctx, B200MVS_ERR_INVALID_ARG, "Invalid master view");
+        if (s->scale >= (int)ctx->views[r].lv.size()) return fail(ctx, B200MVS_ERR_INVALID_ARG, "Invalid scale factor");
+        if (ctx->views[r].lv[s->scale].w > 0xFFFF || ctx->views[r].lv[s->scale].h > 0xFFFF)
+            return fail(ctx, B200MVS_ERR_UNSUPPORTED, "reference level larger than 65535 pixels per side");
+    }
+    if (failed_view) *failed_view = -1;
+    CK(cudaSetDevice(ctx->device));
+    if ((rc = sync_view_params(ctx))) return rc;
+    cudaStream_t st = ctx->stream;
+    const std::time_t t_start = std::time(nullptr);
+    std::memset(ctx->h_counters, 0, sizeof(unsigned long long) * 4096);
+
+    // ---- host phase per view: analyzeFeatures + globalViewSelection + seed list (dmrecon.cc:179-292) ----
+    std::vector<JobParams> jobs(n_refs);
+    std::vector<std::vector<int>> gsels(n_refs);
+    std::vector<Entry> seeds;
+    size_t total_px = 0;
+    std::vector<size_t> px_off(n_refs);
+    for (int j = 0; j < n_refs; ++j) {
+        if (progress) { progress[j].status = 1; progress[j].start_time = (uint64_t)t_start; progress[j].filled = 0; progress[j].queue_size = 0; }
+        gsels[j] = global_view_selection(ctx, *s, refs[j]);
+        if (gsels[j].empty()) {
+            if (failed_view) *failed_view = refs[j];
+            return fail(ctx, B200MVS_ERR_GLOBAL_VS, "Global View Selection failed");
+        }
+        if ((rc = make_job(ctx, *s, refs[j], gsels[j], jobs[j]))) return rc;
+        px_off[j] = total_px;
+        total_px += (size_t)jobs[j].W * jobs[j].H;
+        if (progress) progress[j].status = 2;
+        const std::vector<Seed> sd = collect_seeds(ctx, *s, refs[j], gsels[j]);
+        for (const Seed& q : sd) {
+            Entry e;
+            // a seed outside the image fails in the PatchSampler ctor (patch_sampler.cc:47-50); keep it so that the
+            // processed count matches, the kernel rejects it by the same bounds test
+            const int x = std::min(std::max(q.x, -1), 0xFFFE), y = std::min(std::max(q.y, -1), 0xFFFE);
+            e.xy = (x & 0xFFFF) | ((y & 0xFFFF) << 16);
+            e.jobdir = j | (4 << 24);
+            e.conf = 0.f; e.depth = q.depth; e.dzI = 0.f; e.dzJ = 0.f; e.slots = 0xFFFFFFFFu; e.pad = 0;
+            seeds.push_back(e);
+        }
+        if (stats) stats->n_seeds_processed += sd.size();
+    }
+
+    // ---- device buffers ----
+    const size_t per_px = 4 + 4 + 8 + 12 + 4 + 8;   // depth, conf, dz, normal, slots, sel
+    CK(ctx->maps.reserve(total_px * per_px + 256 * 8));
+    unsigned char* base = ctx->maps.p;
+    {
+        // sel first (8-byte alignment), then the float maps
+        unsigned long long* sel = reinterpret_cast<unsigned long long*>(base);
+        float* depth = reinterpret_cast<float*>(base + total_px * 8);
+        float* conf = depth + total_px;
+        float* dz = conf + total_px;
+        float* normal = dz + 2 * total_px;
+        unsigned* slots = reinterpret_cast<unsigned*>(normal + 3 * total_px);
+        for (int j = 0; j < n_refs; ++j) {
+            jobs[j].sel = sel + px_off[j];
+            jobs[j].depth = depth + px_off[j];
+            jobs[j].conf = conf + px_off[j];
+            jobs[j].dz = dz + 2 * px_off[j];
+            jobs[j].normal = normal + 3 * px_off[j];
+            jobs[j].slots = slots + px_off[j];
+        }
+        CK(cudaMemsetAsync(base, 0, total_px * (per_px - 4), st));               // sel, depth, conf, dz, normal = 0
+        CK(cudaMemsetAsync(slots, 0xFF, total_px * 4, st));
+    }
+    const size_t cap = std::max<size_t>(std::max<size_t>(total_px, seeds.size()), 1u << 16);
+    CK(ctx->ent_a.reserve(cap));
+    CK(ctx->ent_b.reserve(cap));
+    CK(ctx->run_in.reserve(cap));
+    CK(ctx->run_out.reserve(cap));
+    CK(ctx->written.reserve(cap));
+    CK(ctx->counters.reserve(C_NUM + n_refs));
+    CK(ctx->d_jobs.reserve(n_refs));
+    CK(ctx->d_settings.reserve(1));
+    if ((size_t)(C_NUM + n_refs) > 4096) return fail(ctx, B200MVS_ERR_INVALID_ARG, "too many reference views in one batch");
+    const DevSettings ds = to_dev(*s);
+    CK(cudaMemcpyAsync(ctx->d_jobs.p, jobs.data(), sizeof(JobParams) * n_refs, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_settings.p, &ds, sizeof(ds), cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(ctx->counters.p, 0, sizeof(unsigned long long) * (C_NUM + n_refs), st));
+    unsigned long long* d_cnt = ctx->counters.p;
+    unsigned long long* d_filled = d_cnt + C_NUM;
+
+    size_t n_ev = 0;
+    std::vector<std::pair<size_t, size_t>> opt_events;
+    uint64_t launches = 0, opt_launches = 0;
+    cudaEvent_t ev_begin = get_event(ctx, n_ev++);
+    CK(cudaEventRecord(ev_begin, st));
+
+    Entry* cur = ctx->ent_a.p;
+    Entry* nxt = ctx->ent_b.p;
+    size_t n_cur = 0;
+    // ---- seeds: processFeatures (dmrecon.cc:293-326) ----
+    if (!seeds.empty()) {
+        const int ns = (int)seeds.size();
+        CK(cudaMemcpyAsync(ctx->run_in.p, seeds.data(), sizeof(Entry) * ns, cudaMemcpyHostToDevice, st));
+        cudaEvent_t a = get_event(ctx, n_ev), b = get_event(ctx, n_ev + 1);
+        opt_events.push_back({n_ev, n_ev + 1}); n_ev += 2;
+        CK(cudaEventRecord(a, st));
+        k_optimize<<<(ns + OPT_WARPS - 1) / OPT_WARPS, OPT_WARPS * 32, 0, st>>>(ctx->run_in.p, ctx->run_out.p, nullptr, ns, ctx->d_settings.p,
+                                                                              ctx->d_jobs.p, ctx->d_views, ctx->d_lut, d_cnt);
+        CK(cudaEventRecord(b, st));
+        k_seed_select<<<(ns + 255) / 256, 256, 0, st>>>(ctx->run_in.p, ctx->run_out.p, ns, ctx->d_jobs.p, d_cnt);
+        k_seed_commit<<<(ns + 255) / 256, 256, 0, st>>>(ctx->run_in.p, ctx->run_out.p, ns, ctx->d_jobs.p, cur, cap, d_cnt, d_filled);
+        CK(cudaGetLastError());
+        launches += 3; opt_launches += 1;
+        CK(cudaMemcpyAsync(ctx->h_counters, d_cnt, sizeof(unsigned long long) * (C_NUM + n_refs), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        n_cur = (size_t)ctx->h_counters[C_NEXT];
+        if (stats) stats->n_seeds_success = ctx->h_counters[C_SEED_OK];
+    }
+    // ---- processQueue as frontier rounds (dmrecon.cc:334-434; DESIGN.md "Frontier schedule") ----
+    uint64_t rounds = 0, peak = n_cur;
+    bool cancelled = false;
+    while (n_cur > 0) {
+        if (ctx->h_counters[C_OVERFLOW]) return fail(ctx, B200MVS_ERR_OVERFLOW, "frontier buffer overflow (capacity %zu entries)", cap);
+        if (progress) {
+            for (int j = 0; j < n_refs; ++j) {
+                progress[j].status = 3;
+                progress[j].filled = ctx->h_counters[C_NUM + j];
+                progress[j].queue_size = n_cur;
+                if (progress[j].cancelled) cancelled = true;
+            }
+            if (cancelled) break;
+        }
+        ++rounds;
+        peak = std::max<uint64_t>(peak, n_cur);
+        const int n = (int)n_cur;
+        CK(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long) * 2, st));   // C_RUN, C_NEXT
+        k_select<<<(n + 255) / 256, 256, 0, st>>>(cur, n, ctx->d_jobs.p);
+        k_pick<<<(n + 255) / 256, 256, 0, st>>>(cur, n, ctx->d_jobs.p, ctx->run_in.p, nxt, cap, d_cnt);
+        cudaEvent_t a = get_event(ctx, n_ev), b = get_event(ctx, n_ev + 1);
+        opt_events.push_back({n_ev, n_ev + 1}); n_ev += 2;
+        CK(cudaEventRecord(a, st));
+        k_optimize<<<(n + OPT_WARPS - 1) / OPT_WARPS, OPT_WARPS * 32, 0, st>>>(ctx->run_in.p, ctx->run_out.p, d_cnt + C_RUN, n, ctx->d_settings.p,
+                                                                             ctx->d_jobs.p, ctx->d_views, ctx->d_lut, d_cnt);
+        CK(cudaEventRecord(b, st));
+        k_commit<<<(n + 255) / 256, 256, 0, st>>>(ctx->run_in.p, ctx->run_out.p, d_cnt + C_RUN, ctx->d_jobs.p, ctx->written.p, d_cnt, d_filled);
+        k_expand<<<(n + 255) / 256, 256, 0, st>>>(ctx->run_in.p, ctx->run_out.p, ctx->written.p, d_cnt + C_RUN, ctx->d_jobs.p, nxt, cap, d_cnt);
+        CK(cudaGetLastError());
+        launches += 5; opt_launches += 1;
+        CK(cudaMemcpyAsync(ctx->h_counters, d_cnt, sizeof(unsigned long long) * (C_NUM + n_refs), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        n_cur = (size_t)std::min<unsigned long long>(ctx->h_counters[C_NEXT], cap);
+        std::swap(cur, nxt);
+    }
+    if (ctx->h_counters[C_OVERFLOW]) return fail(ctx, B200MVS_ERR_OVERFLOW, "frontier buffer overflow (capacity %zu entries)", cap);
+    cudaEvent_t ev_end = get_event(ctx, n_ev++);
+    CK(cudaEventRecord(ev_end, st));
+
+    // ---- results ----
+    if (maps && !cancelled) {
+        std::vector<unsigned> hslots;
+        for (int j = 0; j < n_refs; ++j) {
+            const size_t np = (size_t)jobs[j].W * jobs[j].H;
+            maps[j].width = jobs[j].W; maps[j].height = jobs[j].H;
+            if (progress) progress[j].status = 4;
+            if (maps[j].depth) CK(cudaMemcpyAsync(maps[j].depth, jobs[j].depth, np * 4, cudaMemcpyDeviceToHost, st));
+            if (maps[j].conf) CK(cudaMemcpyAsync(maps[j].conf, jobs[j].conf, np * 4, cudaMemcpyDeviceToHost, st));
+            if (maps[j].dz) CK(cudaMemcpyAsync(maps[j].dz, jobs[j].dz, np * 8, cudaMemcpyDeviceToHost, st));
+            if (maps[j].normal) CK(cudaMemcpyAsync(maps[j].normal, jobs[j].normal, np * 12, cudaMemcpyDeviceToHost, st));
+            if (maps[j].view_ids) {
+                hslots.resize(np);
+                CK(cudaMemcpyAsync(hslots.data(), jobs[j].slots, np * 4, cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+                const std::vector<int>& g = gsels[j];
+                for (size_t p = 0; p < np; ++p)
+                    for (int k = 0; k < 4; ++k) {
+                        const unsigned sl = (hslots[p] >> (8 * k)) & 0xFF;
+                        maps[j].view_ids[4 * p + k] = (sl < g.size()) ? g[sl] : -1;
+                    }
+            }
+        }
+    }
+    CK(cudaStreamSynchronize(st));
+    uint64_t filled = 0;
+    for (int j = 0; j < n_refs; ++j) {
+        filled += ctx->h_counters[C_NUM + j];
+        if (progress) { progress[j].filled = ctx->h_counters[C_NUM + j]; progress[j].queue_size = 0; progress[j].status = cancelled ? 5 : 0; }
+    }
+    if (stats) {
+        stats->n_opt = ctx->h_counters[C_OPTS];
+        stats->n_sample_sets = ctx->h_counters[C_SETS];
+        stats->n_rounds = rounds;
+        stats->n_filled = filled;
+        stats->n_entries_peak = peak;
+        stats->n_patch_launches = opt_launches;
+        stats->n_kernel_launches = launches;
+        double ms_opt = 0.0;
+        for (auto& pr : opt_events) { float ms = 0.f; cudaEventElapsedTime(&ms, ctx->ev_pool[pr.first], ctx->ev_pool[pr.second]); ms_opt += ms; }
+        float ms_all = 0.f;
+        cudaEventElapsedTime(&ms_all, ev_begin, ev_end);
+        stats->ms_patch_kernel = ms_opt;
+        stats->ms_total_device = ms_all;
+    }
+    if (cancelled) return fail(ctx, B200MVS_ERR_CANCELLED, "reconstruction cancelled");
+    return 0;
+}
+
+} // extern "C"
