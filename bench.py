@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""bench.py - MVS depth-pixels/second of the dmrecon hot path on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (one rank per GPU under torchrun for N > 1)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU dmrecon on the host cores
+
+Workload (N = 1): BASELINE.json configs[1] - synthetic 16-view 1920x1080 scene, dmrecon scale = 1, all 16 views
+reconstructed; one step = DMRecon::start for all 16 reference views.  N > 1: the same per-GPU work (16 reference
+views per rank, weak scaling) on a 16N-view scene; every rank renders and uploads its own shard and the images of the
+other shards arrive through one NCCL all-gather (the reference path has no other cross-view exchange).
+
+value  = depth-pixels (pixels ending with conf > 0, = progress.filled) per second with the image pyramids already
+         resident in HBM, results left in HBM, summed over all ranks / max-over-ranks time.
+e2e    = the same metric through the public API with HOST buffers: pinned host images -> device (+ all-gather),
+         pyramids, reconstruction, depth/conf/dz maps -> pinned host memory, every step.
+roofline, cpu_baseline: see DESIGN.md "Measurement".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "mvs_depth_pixels_per_second"
+UNIT = "depth-pixels/s"
+VIEWS_PER_GPU = 16
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def workload_cfg(name, n_gpus):
+    from mve_b200 import synth
+    cfg = dict(synth.CONFIGS[name])
+    if name == "C2" and n_gpus > 1:
+        cfg["views"] = VIEWS_PER_GPU * n_gpus
+        cfg["grid"] = (4 * n_gpus, 4)
+        cfg["features"] = 4000 * n_gpus
+    cfg["name"] = name
+    return cfg
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+            except Exception:
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the reference's own CPU implementation, time-boxed
+# ----------------------------------------------------------------------------------------------------------------
+def write_scene_for_reference(cfg, views, tmp):
+    """Writes the workload as an MVE scene directory (views/*.mve + synth_0.out) for the unmodified reference."""
+    from mve_b200 import synth
+    s = synth.make_scene(cfg, device="cuda" if _cuda_ok() else None)
+    synth.write_mve_scene(s, tmp)
+    return s
+
+
+def _cuda_ok():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def run_reference_sample(scene_dir, scene, seconds, views):
+    """One bounded sample of the reference CPU path. Returns (filled_px, elapsed_s, threads, kind, sample_text)."""
+    harness = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
+    if os.path.exists(harness):
+        cmd = [harness, "timed", scene_dir, str(scene.scale), str(scene.nr_recon_neighbors), "%.3f" % seconds] + [str(v) for v in views]
+        out = subprocess.run(cmd, capture_output=True, text=True, check=True).stdout.strip().splitlines()[-1]
+        r = json.loads(out)
+        return r["filled"], r["seconds"], len(views), "reference", \
+            "oracle/_ref/ref_harness timed: mvs::DMRecon::start of %d reference views on %d host threads (one per view, " \
+            "apps/dmrecon.cc:285), cancelled after %.1f s through Progress::cancelled; images pre-loaded" % (len(views), len(views), seconds)
+    # the compiled reference is not here: fall back to the CPU port, one thread per view
+    from oracle import oracle_py as O
+    osc = O.OracleScene(scene)
+    st = O.default_settings(scale=scene.scale, nr_recon_neighbors=scene.nr_recon_neighbors)
+    filled = [0] * len(views)
+
+    def work(k, v):
+        filled[k] = int(osc.reconstruct(st, v, max_seconds=seconds)["stats"]["n_filled"])
+    t0 = time.time()
+    th = [threading.Thread(target=work, args=(k, v)) for k, v in enumerate(views)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    return sum(filled), time.time() - t0, len(views), "port", \
+        "oracle/mvs_oracle.cc port, %d views on %d threads, stopped after %.1f s" % (len(views), len(views), seconds)
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cfg = workload_cfg(args.workload, 1)
+    cores = host_cores()
+    budget = min(20.0, max(3.0, 150.0 / max(1, args.steps + args.warmup)))
+    with tempfile.TemporaryDirectory(prefix="b200mvs_ref_") as tmp:
+        t = time.time()
+        scene = write_scene_for_reference(cfg, None, tmp)
+        log("reference arm: scene written in %.1fs, %d host cores, %.1fs per step" % (time.time() - t, cores, budget))
+        views = list(range(min(scene.n_views, cores)))
+        vals, secs = [], []
+        for i in range(args.warmup + args.steps):
+            filled, el, threads, kind, sample = run_reference_sample(tmp, scene, budget, views)
+            log("  step %d: %d px in %.2fs" % (i, filled, el))
+            if i >= args.warmup:
+                vals.append(filled); secs.append(el)
+    value = sum(vals) / sum(secs)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * sum(secs) / len(secs), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "%s: synthetic %d-view %dx%d scene, dmrecon scale=%d" % (args.workload, scene.n_views, scene.width, scene.height, scene.scale),
+                       "step": "time-boxed sample of the same workload (reference cannot finish a step within the run budget)"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample,
+                             "host_cores_available": cores},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="C2")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    from mve_b200 import dmrecon, sharding, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        log("warning: WORLD_SIZE=%d but --gpus %d; using WORLD_SIZE" % (world, args.gpus))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg = workload_cfg(args.workload, world)
+    owned = sharding.owned_views(cfg["views"], rank, world)
+    t0 = time.time()
+    scene = synth.make_scene(cfg, device=str(dev), only_views=owned)
+    log("[rank %d] scene %s: %d views (%d owned) generated in %.1fs" % (rank, args.workload, scene.n_views, len(owned), time.time() - t0))
+    H, W = scene.height, scene.width
+
+    # pinned host staging of the owned images (the e2e input) and of the result maps (the e2e output)
+    host_imgs = torch.empty((len(owned), H, W, 3), dtype=torch.uint8).pin_memory()
+    for k, v in enumerate(owned):
+        host_imgs[k].copy_(torch.from_numpy(scene.images[v]))
+    settings = dmrecon.Settings(scale=scene.scale, nr_recon_neighbors=scene.nr_recon_neighbors)
+    gscene = dmrecon.Scene(scene.n_views, device=local)
+    gscene.set_features(scene.feat_pos, scene.feat_refs)
+
+    def upload_all():
+        """pinned host -> device for the owned views, all-gather of the image shards, pyramids on device."""
+        dimgs = host_imgs.to(dev, non_blocking=True)
+        all_imgs = sharding.all_gather_images(dimgs, world)          # [V, H, W, 3] on every rank
+        torch.cuda.synchronize()
+        for v in range(scene.n_views):
+            gscene.set_view_device(v, all_imgs[v].data_ptr(), W, H, scene.flen[v], scene.paspect[v], scene.ppoint[v],
+                                   scene.rot[v], scene.trans[v])
+        return all_imgs
+
+    upload_all()
+    Ws, Hs = W, H
+    for _ in range(scene.scale):
+        Ws, Hs = (Ws + 1) // 2, (Hs + 1) // 2
+    out_bufs = []
+    for _ in owned:
+        out_bufs.append(dict(depth=torch.empty((Hs, Ws), dtype=torch.float32).pin_memory().numpy(),
+                             conf=torch.empty((Hs, Ws), dtype=torch.float32).pin_memory().numpy(),
+                             dz=torch.empty((Hs, Ws, 2), dtype=torch.float32).pin_memory().numpy()))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        flush.zero_()
+        _, st = gscene.reconstruct(settings, owned, download=False)
+        return st
+
+    def step_e2e():
+        flush.zero_()
+        upload_all()
+        _, st = gscene.reconstruct(settings, owned, download=True, out=out_bufs)
+        return st
+
+    def agg(x):
+        if world == 1:
+            return float(x), float(x)
+        t = torch.tensor([float(x)], dtype=torch.float64, device=dev)
+        s = t.clone(); dist.all_reduce(s, op=dist.ReduceOp.SUM)
+        m = t.clone(); dist.all_reduce(m, op=dist.ReduceOp.MAX)
+        return float(s.item()), float(m.item())
+
+    # ---- HBM-resident timing (value) ----
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    stats = []
+    with ClockSampler(local) as clk:
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            stats.append(step_resident())
+        barrier()
+        elapsed = time.perf_counter() - t0
+    clocks = clk.summary()
+    filled_local = sum(int(s.n_filled) for s in stats)
+    filled_total, _ = agg(filled_local)
+    _, elapsed_max = agg(elapsed)
+    _, dev_ms_max = agg(sum(s.ms_total_device for s in stats))
+    value = filled_total / elapsed_max
+    launches_total, _ = agg(sum(int(s.n_kernel_launches) for s in stats))
+
+    # ---- end to end through the host-buffer API ----
+    e2e_steps = max(1, min(args.steps, 3))
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    f_e2e = 0
+    for _ in range(e2e_steps):
+        f_e2e += int(step_e2e().n_filled)
+    barrier()
+    e2e_elapsed = time.perf_counter() - t0
+    f_e2e_total, _ = agg(f_e2e)
+    _, e2e_max = agg(e2e_elapsed)
+    h2d = int(host_imgs.numel())
+    d2h = int(sum(b["depth"].nbytes + b["conf"].nbytes + b["dz"].nbytes for b in out_bufs))
+
+    # ---- roofline of the dominant kernel (k_optimize), rank 0 ----
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
+    consts = {}
+    try:
+        consts = json.load(open(os.path.join(ROOT, "profiles", "scene_constants_%s.json" % args.workload)))
+    except Exception:
+        pass
+    bpp = float(consts.get("bytes_alg_per_filled_px", 0.0))
+    ms_kernel = sum(s.ms_patch_kernel for s in stats)
+    n_launch = sum(int(s.n_patch_launches) for s in stats)
+    achieved = (bpp * filled_local / (ms_kernel * 1e-3)) / 1e9 if ms_kernel > 0 and bpp > 0 else None
+    roofline = {"kernel": "k_optimize (patch optimisation, one warp per queue entry)", "bound": "hbm",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+                "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_filled_px": bpp,
+                "definition": "300 B x N_PSE + 75 B x N_opt + 28 B x N_filled with the oracle's strict-order counts per filled "
+                              "pixel (profiles/scene_constants_%s.json) x filled pixels of the launch, / CUDA-event time of the "
+                              "k_optimize launches in the timed region" % args.workload,
+                "avg_launch_ms": ms_kernel / max(1, n_launch), "launches": n_launch,
+                "kernel_share_of_device_time": ms_kernel / max(1e-9, sum(s.ms_total_device for s in stats)),
+                "impl_sample_sets": sum(int(s.n_sample_sets) for s in stats), "impl_opts": sum(int(s.n_opt) for s in stats),
+                "impl_bytes_300_per_set_GBs": (300.0 * sum(int(s.n_sample_sets) for s in stats) / (ms_kernel * 1e-3) / 1e9) if ms_kernel > 0 else None}
+
+    # ---- cpu_baseline (rank 0, N = 1 only): the reference's own CPU dmrecon on this box's host cores ----
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            full = synth.make_scene(cfg, device=str(dev))
+            with tempfile.TemporaryDirectory(prefix="b200mvs_cpu_") as tmp:
+                synth.write_mve_scene(full, tmp)
+                cores = host_cores()
+                views = list(range(min(full.n_views, cores)))
+                filled, el, threads, kind, sample = run_reference_sample(tmp, full, args.cpu_seconds, views)
+            cpu_baseline = {"value": filled / el, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample,
+                            "host_cores_available": cores}
+        except Exception as ex:   # the GPU numbers stand on their own
+            cpu_baseline = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(ex)}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": 1e3 * elapsed_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "%s: synthetic %d-view %dx%d scene, dmrecon scale=%d, %d reference views per GPU" %
+                                       (args.workload, scene.n_views, W, H, scene.scale, len(owned)),
+                           "sharding": "reference views block-sharded over ranks; image shards exchanged by one NCCL all-gather" if world > 1 else "single GPU",
+                           "l2": "256 MiB buffer written between steps (L2 flush); the pyramids alone (%.0f MB) exceed the 126 MB L2" %
+                                 (scene.n_views * W * H * 4 * 4 / 3 / 1e6),
+                           "filled_px_per_step": filled_total / args.steps, "swept_px_per_step": world * len(owned) * Ws * Hs,
+                           "device_ms_per_step_max": dev_ms_max / args.steps},
+                "clocks": clocks, "gpu_launches": int(launches_total),
+                "e2e": {"value": f_e2e_total / e2e_max, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "steps": e2e_steps, "ms_per_step": 1e3 * e2e_max / e2e_steps},
+                "roofline": roofline, "cpu_baseline": cpu_baseline}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -207,8 +207,9 @@ class Scene:
         return out
 
     def reconstruct(self, settings: Settings, ref_views: Sequence[int], download: bool = True,
-                    want=("depth", "conf", "dz", "normal", "view_ids")):
-        """DMRecon::start for a batch of reference views. Returns (list of map dicts or None, Stats)."""
+                    want=("depth", "conf", "dz", "normal", "view_ids"), out=None):
+        """DMRecon::start for a batch of reference views. Returns (list of map dicts or None, Stats).
+        out: optional list (one dict per view) of preallocated host arrays (e.g. pinned) to receive the maps."""
         refs = np.asarray(ref_views, np.int32)
         n = len(refs)
         stats = Stats()
@@ -222,6 +223,15 @@ class Scene:
                 w, h = C.c_int(), C.c_int()
                 self._check(self._lib.b200mvs_get_level(self._h, int(r), settings.scale, C.byref(w), C.byref(h), None))
                 W, H = w.value, h.value
+                if out is not None:
+                    d = out[j]
+                    for k, a in d.items():
+                        if a.shape[:2] != (H, W) or not a.flags["C_CONTIGUOUS"]:
+                            raise ValueError("out[%d][%s] has the wrong shape" % (j, k))
+                    results.append(d)
+                    for k in ("depth", "conf", "dz", "normal", "view_ids"):
+                        setattr(maps_arr[j], k, d[k].ctypes.data if k in d else None)
+                    continue
                 d = dict(depth=np.empty((H, W), np.float32))
                 if "conf" in want:
                     d["conf"] = np.empty((H, W), np.float32)

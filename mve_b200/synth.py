@@ -74,7 +74,7 @@ CONFIGS: Dict[str, Dict] = {
                surface="bumps", features=300, scale=0),
     "T1": dict(seed=12, views=9, width=320, height=240, layout="grid", grid=(3, 3), pitch=0.8,
                surface="bumps", features=600, scale=1),
-    "T2": dict(seed=13, views=12, width=200, height=150, layout="orbit", surface="sphere",
+    "T2": dict(seed=13, views=12, width=160, height=120, layout="orbit", surface="sphere",
                features=800, scale=0, orbit_views_per_ring=6),
 }
 
@@ -163,8 +163,9 @@ def _look_at(cpos: np.ndarray, target: np.ndarray, down=np.array([0.0, 1.0, 0.0]
     return np.stack([r, d, f])  # rows: camera x (right), y (down), z (forward)
 
 
-def make_scene(config, device: Optional[str] = None, **overrides) -> Scene:
-    """Build a synthetic scene. `config` is a key of CONFIGS or a dict."""
+def make_scene(config, device: Optional[str] = None, only_views=None, **overrides) -> Scene:
+    """Build a synthetic scene. `config` is a key of CONFIGS or a dict.
+    only_views: render only these views' images (the others are None) - used when ranks render their own shard."""
     name = config if isinstance(config, str) else config.get("name", "custom")
     cfg = dict(CONFIGS[config]) if isinstance(config, str) else dict(config)
     cfg.update(overrides)
@@ -213,6 +214,9 @@ def make_scene(config, device: Optional[str] = None, **overrides) -> Scene:
     ys, xs = torch.meshgrid(torch.arange(H, dtype=torch.float64, device=dev),
                             torch.arange(W, dtype=torch.float64, device=dev), indexing="ij")
     for v in range(V):
+        if only_views is not None and v not in only_views:
+            images.append(None)
+            continue
         R = torch.as_tensor(rot32[v].astype(np.float64).reshape(3, 3), device=dev)
         C = -(R.T @ torch.as_tensor(trans32[v].astype(np.float64), device=dev))
         # pixel centre (x+.5, y+.5) -> camera ray (libs/mve/depthmap.cc:149-156)
@@ -233,7 +237,8 @@ def make_scene(config, device: Optional[str] = None, **overrides) -> Scene:
         p = p / np.linalg.norm(p, axis=1, keepdims=True) * surf.radius
         nrm = p / surf.radius
     else:
-        xy = rng.uniform(-2.6, 2.6, size=(F, 2)) * np.array([1.0, H / W * 1.3])
+        ext = np.abs(pos[:, :2]).max(axis=0) + 0.32 * dist * np.array([1.0, H / W])
+        xy = rng.uniform(-1.0, 1.0, size=(F, 2)) * ext
         z = surf.height(torch.as_tensor(xy[:, 0]), torch.as_tensor(xy[:, 1])).numpy()
         p = np.concatenate([xy, z[:, None]], 1)
         nrm = None
@@ -338,3 +343,26 @@ def write_mve_scene(scene: Scene, path: str) -> None:
             for r in refs:
                 f.write(" %d 0 0" % int(r))
             f.write("\n")
+
+
+# ----------------------------------------------------------------------------
+# self-contained scene files (used for committed test fixtures)
+# ----------------------------------------------------------------------------
+def save_scene_npz(scene: Scene, path: str) -> None:
+    off = np.zeros(len(scene.feat_refs) + 1, np.int32)
+    off[1:] = np.cumsum([len(r) for r in scene.feat_refs])
+    ids = np.concatenate(scene.feat_refs).astype(np.int32) if scene.feat_refs else np.zeros(0, np.int32)
+    np.savez_compressed(path, name=scene.name, images=np.stack(scene.images), flen=scene.flen, paspect=scene.paspect,
+                        ppoint=scene.ppoint, rot=scene.rot, trans=scene.trans, feat_pos=scene.feat_pos,
+                        feat_off=off, feat_ids=ids, scale=scene.scale, nr_recon_neighbors=scene.nr_recon_neighbors)
+
+
+def load_scene_npz(path: str) -> Scene:
+    z = np.load(path, allow_pickle=False)
+    imgs = z["images"]
+    off, ids = z["feat_off"], z["feat_ids"]
+    refs = [ids[off[i]:off[i + 1]].astype(np.int32) for i in range(len(off) - 1)]
+    return Scene(name=str(z["name"]), width=imgs.shape[2], height=imgs.shape[1], images=[imgs[i] for i in range(len(imgs))],
+                 flen=z["flen"], paspect=z["paspect"], ppoint=z["ppoint"], rot=z["rot"], trans=z["trans"],
+                 feat_pos=z["feat_pos"], feat_refs=refs, scale=int(z["scale"]),
+                 nr_recon_neighbors=int(z["nr_recon_neighbors"]))

@@ -1,0 +1,192 @@
+/* TEST INFRASTRUCTURE - NOT PRODUCT CODE.
+ *
+ * Our own driver around the UNMODIFIED reference classes (linked from oracle/_ref/libmve_dmrecon.a,
+ * libmve.a, libmve_util.a, built by oracle/Makefile from /root/reference).  It never re-implements the
+ * algorithm; it only calls the reference's public interface:
+ *
+ *   ref_harness patches SCENE REF SCALE NRN IN.bin OUT.bin
+ *       Mints per-patch golden vectors: builds the SingleViews like DMRecon's ctor (dmrecon.cc:62-79),
+ *       runs analyzeFeatures' loop (dmrecon.cc:179-208) + mvs::GlobalViewSelection, then one
+ *       mvs::PatchOptimization (ctor + doAutoOptimization + computeConfidence, exactly the three calls of
+ *       dmrecon.cc:293-296 / :374-377) per record of IN.bin and writes the results to OUT.bin.
+ *       Record layouts = mvs_oracle_patch_in / mvs_oracle_patch_out of oracle/mvs_oracle.h.
+ *
+ *   ref_harness timed SCENE SCALE NRN SECONDS VIEW [VIEW...]
+ *       CPU baseline: runs mvs::DMRecon(scene, settings).start() for the listed views, one thread per view
+ *       (the reference's own parallelism, apps/dmrecon/dmrecon.cc:285), sets Progress::cancelled after
+ *       SECONDS (the reference's cooperative cancel, dmrecon.cc:353) and prints one JSON line with the
+ *       filled pixel counts and the elapsed time.  SECONDS <= 0 runs to completion.
+ */
+#include <atomic>
+#include <chrono>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "dmrecon/dmrecon.h"
+#include "dmrecon/global_view_selection.h"
+#include "dmrecon/patch_optimization.h"
+#include "dmrecon/settings.h"
+#include "dmrecon/single_view.h"
+#include "math/octree_tools.h"
+#include "mve/scene.h"
+
+#include "mvs_oracle.h"
+
+static int run_patches(int argc, char** argv)
+{
+    if (argc != 8) { std::fprintf(stderr, "usage: ref_harness patches SCENE REF SCALE NRN IN OUT\n"); return 2; }
+    mve::Scene::Ptr scene = mve::Scene::create(argv[2]);
+    mvs::Settings settings;
+    settings.refViewNr = std::atoi(argv[3]);
+    settings.scale = std::atoi(argv[4]);
+    settings.nrReconNeighbors = std::atoi(argv[5]);
+    settings.quiet = true;
+    mve::Bundle::ConstPtr bundle = scene->get_bundle();
+    mve::Scene::ViewList const& mve_views(scene->get_views());
+    std::vector<mvs::SingleView::Ptr> views(mve_views.size());
+    for (std::size_t i = 0; i < mve_views.size(); ++i) {
+        if (mve_views[i] == nullptr || !mve_views[i]->is_camera_valid()
+            || !mve_views[i]->has_image(settings.imageEmbedding, mve::IMAGE_TYPE_UINT8))
+            continue;
+        views[i] = mvs::SingleView::create(scene, mve_views[i], settings.imageEmbedding);
+    }
+    mvs::SingleView::Ptr refV = views[settings.refViewNr];
+    refV->loadColorImage(settings.scale);
+    refV->prepareMasterView(settings.scale);
+    mve::Bundle::Features const& features = bundle->get_features();
+    for (std::size_t i = 0; i < features.size(); ++i) {
+        if (!features[i].contains_view_id(settings.refViewNr)) continue;
+        math::Vec3f featurePos(features[i].pos);
+        if (!refV->pointInFrustum(featurePos)) continue;
+        if (!math::geom::point_box_overlap(featurePos, settings.aabbMin, settings.aabbMax)) continue;
+        for (std::size_t j = 0; j < features[i].refs.size(); ++j) {
+            int view_id = features[i].refs[j].view_id;
+            if (view_id < 0 || view_id >= static_cast<int>(views.size()) || views[view_id] == nullptr) continue;
+            if (views[view_id]->pointInFrustum(featurePos)) views[view_id]->addFeature(i);
+        }
+    }
+    mvs::GlobalViewSelection globalVS(views, features, settings);
+    globalVS.performVS();
+    mvs::IndexSet neighViews = globalVS.getSelectedIDs();
+    std::printf("Global View Selection:");
+    for (std::size_t id : neighViews) std::printf(" %zu", id);
+    std::printf("\n");
+    for (std::size_t id : neighViews) views[id]->loadColorImage(0);
+
+    std::ifstream in(argv[6], std::ios::binary);
+    std::vector<char> buf((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+    const std::size_t n = buf.size() / sizeof(mvs_oracle_patch_in);
+    const mvs_oracle_patch_in* pin = reinterpret_cast<const mvs_oracle_patch_in*>(buf.data());
+    std::vector<mvs_oracle_patch_out> pout(n);
+    for (std::size_t i = 0; i < n; ++i) {
+        mvs::IndexSet local;
+        for (int k = 0; k < pin[i].n_local; ++k) local.insert(pin[i].local_ids[k]);
+        mvs_oracle_patch_out& o = pout[i];
+        std::memset(&o, 0, sizeof(o));
+        for (int k = 0; k < 4; ++k) o.local_ids[k] = -1;
+        mvs::PatchOptimization patch(views, settings, pin[i].x, pin[i].y, pin[i].depth, pin[i].dz_i, pin[i].dz_j,
+            neighViews, local);
+        patch.doAutoOptimization();
+        o.conf = patch.computeConfidence();
+        o.depth = patch.getDepth();
+        o.dz_i = patch.getDzI();
+        o.dz_j = patch.getDzJ();
+        if (o.conf > 0.f) {
+            math::Vec3f nrm = patch.getNormal();
+            o.normal[0] = nrm[0]; o.normal[1] = nrm[1]; o.normal[2] = nrm[2];
+        }
+        int k = 0;
+        for (std::size_t id : patch.getLocalViewIDs()) { if (k < 4) o.local_ids[k] = (int)id; ++k; }
+        o.n_local = k;
+        o.iterations = -1;           /* Status is private in the reference */
+        o.converged = o.conf != 0.f; /* computeConfidence returns 0 unless converged (patch_optimization.cc:117) */
+        o.opti_success = -1;
+    }
+    std::ofstream out(argv[7], std::ios::binary);
+    out.write(reinterpret_cast<const char*>(pout.data()), (std::streamsize)(n * sizeof(mvs_oracle_patch_out)));
+    return 0;
+}
+
+static int run_timed(int argc, char** argv)
+{
+    if (argc < 7) { std::fprintf(stderr, "usage: ref_harness timed SCENE SCALE NRN SECONDS VIEW...\n"); return 2; }
+    mve::Scene::Ptr scene = mve::Scene::create(argv[2]);
+    const int scale = std::atoi(argv[3]);
+    const int nrn = std::atoi(argv[4]);
+    const double seconds = std::atof(argv[5]);
+    std::vector<int> ids;
+    for (int i = 6; i < argc; ++i) ids.push_back(std::atoi(argv[i]));
+    scene->get_bundle();
+    /* touch the input images first so that the timed part is reconstruction, not file I/O */
+    for (int id : ids) scene->get_views()[id]->get_byte_image("undistorted");
+    std::vector<mvs::DMRecon*> recons(ids.size(), nullptr);
+    std::vector<std::size_t> filled(ids.size(), 0);
+    std::vector<int> done(ids.size(), 0);
+    std::atomic<int> running((int)ids.size());
+    std::mutex mtx;
+    auto t0 = std::chrono::steady_clock::now();
+    std::vector<std::thread> th;
+    for (std::size_t k = 0; k < ids.size(); ++k) {
+        th.emplace_back([&, k]() {
+            try {
+                mvs::Settings settings;
+                settings.refViewNr = ids[k];
+                settings.scale = scale;
+                settings.nrReconNeighbors = nrn;
+                settings.quiet = true;
+                settings.keepDzMap = true;
+                settings.keepConfidenceMap = true;
+                mvs::DMRecon recon(scene, settings);
+                { std::lock_guard<std::mutex> lk(mtx); recons[k] = &recon; }
+                recon.start();
+                std::lock_guard<std::mutex> lk(mtx);
+                filled[k] = recon.getProgress().filled;
+                done[k] = recon.getProgress().cancelled ? 0 : 1;
+                recons[k] = nullptr;
+            } catch (std::exception& e) {
+                std::fprintf(stderr, "view %d failed: %s\n", ids[k], e.what());
+                std::lock_guard<std::mutex> lk(mtx);
+                recons[k] = nullptr;
+            }
+            running--;
+        });
+    }
+    if (seconds > 0) {
+        while (running.load() > 0) {
+            std::this_thread::sleep_for(std::chrono::milliseconds(20));
+            double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            if (el >= seconds) {
+                std::lock_guard<std::mutex> lk(mtx);
+                for (std::size_t k = 0; k < ids.size(); ++k) {
+                    mvs::DMRecon* r = recons[k];
+                    if (r) r->getProgress().cancelled = true;
+                }
+                break;
+            }
+        }
+    }
+    for (auto& t : th) t.join();
+    double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    std::size_t total = 0;
+    int complete = 0;
+    for (std::size_t k = 0; k < ids.size(); ++k) { total += filled[k]; complete += done[k]; }
+    std::printf("{\"filled\": %zu, \"seconds\": %.6f, \"views\": %zu, \"views_completed\": %d, \"threads\": %zu}\n",
+                total, el, ids.size(), complete, ids.size());
+    return 0;
+}
+
+int main(int argc, char** argv)
+{
+    if (argc >= 2 && std::strcmp(argv[1], "patches") == 0) return run_patches(argc, argv);
+    if (argc >= 2 && std::strcmp(argv[1], "timed") == 0) return run_timed(argc, argv);
+    std::fprintf(stderr, "usage: ref_harness patches|timed ...\n");
+    return 2;
+}

@@ -1,0 +1,144 @@
+"""Size-independent properties of the GPU path (-m gpu), also at a BASELINE-sized view, plus the error behaviour
+of the C ABI (mirrors the exceptions of libs/dmrecon/dmrecon.cc:37-75,222-223)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from tests.util import golden_scene
+
+pytestmark = pytest.mark.gpu
+
+
+def _gt_depth(scene, view, scale):
+    """Analytic ground truth: distance along each pixel's ray to the synthetic surface (mve_b200.synth)."""
+    import torch
+    from mve_b200 import synth
+    cfg = scene.meta
+    surf = synth._Surface(cfg["surface"], np.random.default_rng(0))
+    W0, H0 = scene.width, scene.height
+    W, H = W0, H0
+    for _ in range(scale):
+        W, H = (W + 1) // 2, (H + 1) // 2
+    R = torch.as_tensor(scene.rot[view].astype(np.float64).reshape(3, 3))
+    Cc = -(R.T @ torch.as_tensor(scene.trans[view].astype(np.float64)))
+    ax = float(scene.flen[view]) * max(W, H)
+    ys, xs = torch.meshgrid(torch.arange(H, dtype=torch.float64), torch.arange(W, dtype=torch.float64), indexing="ij")
+    d = torch.stack([(xs + 0.5 - 0.5 * W) / ax, (ys + 0.5 - 0.5 * H) / ax, torch.ones_like(xs)], -1) @ R
+    d = d / d.norm(dim=-1, keepdim=True)
+    pts, valid = surf.intersect(Cc, d)
+    return (pts - Cc).norm(dim=-1).numpy()
+
+
+def test_full_size_view_properties():
+    """One 1920x1080 reference view at scale 1 (BASELINE config C2 geometry, 9 views): structural invariants,
+    ground-truth accuracy and the fixed-point property of the result."""
+    from mve_b200 import dmrecon, synth
+    s = synth.make_scene("C2", views=9, grid=(3, 3), features=1500)
+    g = dmrecon.Scene.from_synth(s)
+    gs = dmrecon.Settings(scale=1)
+    maps, st = g.reconstruct(gs, [4])
+    m = maps[0]
+    H, W = m["depth"].shape
+    assert (W, H) == (960, 540)
+    filled = m["conf"] > 0
+    assert filled.mean() > 0.6
+    assert int(st.n_filled) == int(filled.sum())
+    # depth > 0 exactly where conf > 0; confidence is (mean NCC - 0.6) / 0.4 in (0, 1]
+    assert ((m["depth"] > 0) == filled).all()
+    assert m["conf"].max() <= 1.0 + 1e-6 and m["conf"].min() >= 0.0
+    # border band of 2 px is never reconstructed (patch_sampler.cc:47-50)
+    assert not filled[:2].any() and not filled[-2:].any() and not filled[:, :2].any() and not filled[:, -2:].any()
+    # exactly nrReconNeighbors distinct, ascending local views from the global selection on every filled pixel
+    ids = m["view_ids"][filled]
+    assert (ids >= 0).all() and (np.diff(ids, axis=1) > 0).all()
+    assert set(np.unique(ids)).issubset(set(g.global_view_selection(gs, 4)))
+    # unit normals facing the camera
+    n = m["normal"][filled]
+    assert np.allclose(np.linalg.norm(n, axis=1), 1.0, atol=1e-4)
+    # accuracy against the analytic surface
+    gt = _gt_depth(s, 4, 1)
+    err = np.abs(m["depth"] - gt)[filled] / gt[filled]
+    assert np.median(err) < 1e-3 and np.percentile(err, 99) < 1e-2
+    # fixed point: re-optimising filled pixels from their own result converges again to (nearly) the same state
+    ys, xs = np.nonzero(filled)
+    pick = np.random.default_rng(3).choice(len(ys), 4000, replace=False)
+    pin = np.zeros(len(pick), dmrecon.PATCH_IN)
+    pin["x"], pin["y"] = xs[pick], ys[pick]
+    pin["depth"] = m["depth"][ys[pick], xs[pick]]
+    pin["dz_i"], pin["dz_j"] = m["dz"][ys[pick], xs[pick], 0], m["dz"][ys[pick], xs[pick], 1]
+    pin["n_local"] = 4
+    pin["local_ids"] = m["view_ids"][ys[pick], xs[pick]]
+    out = g.optimize_patches(gs, 4, g.global_view_selection(gs, 4), pin)
+    ok = out["conf"] > 0
+    assert ok.mean() > 0.98
+    assert np.percentile(np.abs(out["depth"] - pin["depth"])[ok] / pin["depth"][ok], 99) < 2e-3
+    assert np.percentile(np.abs(out["conf"][ok] - m["conf"][ys[pick], xs[pick]][ok]), 99) < 2e-2
+    # idempotence of the whole run
+    maps2, _ = g.reconstruct(gs, [4])
+    assert (maps2[0]["depth"] == m["depth"]).all() and (maps2[0]["conf"] == m["conf"]).all()
+
+
+def test_error_behaviour():
+    from mve_b200 import dmrecon
+    s = golden_scene("T0")
+    g = dmrecon.Scene.from_synth(s)
+    ok = dmrecon.Settings()
+    with pytest.raises(dmrecon.B200MVSError) as e:
+        g.reconstruct(ok, [99])
+    assert e.value.code == -1 and "Master view index out of bounds" in str(e.value)        # dmrecon.cc:37-38
+    with pytest.raises(dmrecon.B200MVSError) as e:
+        g.reconstruct(dmrecon.Settings(scale=-1), [0])
+    assert "Invalid scale factor" in str(e.value)                                           # dmrecon.cc:41-42
+    with pytest.raises(dmrecon.B200MVSError) as e:
+        g.reconstruct(dmrecon.Settings(scale=9), [0])
+    assert "Invalid scale factor" in str(e.value)
+    with pytest.raises(dmrecon.B200MVSError) as e:
+        g.reconstruct(dmrecon.Settings(filter_width=7), [0])
+    assert e.value.code == -6
+    with pytest.raises(dmrecon.B200MVSError) as e:
+        g.reconstruct(dmrecon.Settings(nr_recon_neighbors=5), [0])
+    assert e.value.code == -6
+    # a scene whose features never reference the master view: "Global View Selection failed" (dmrecon.cc:222-223)
+    g2 = dmrecon.Scene.from_synth(s)
+    g2.set_features(s.feat_pos[:3], [np.array([1, 2], np.int32)] * 3)
+    with pytest.raises(dmrecon.B200MVSError) as e:
+        g2.reconstruct(ok, [0])
+    assert e.value.code == -3 and "Global View Selection failed" in str(e.value)
+    # a view that was never uploaded is an invalid master view (dmrecon.cc:73-75)
+    g3 = dmrecon.Scene(3)
+    with pytest.raises(dmrecon.B200MVSError) as e:
+        g3.reconstruct(ok, [0])
+    assert "Invalid master view" in str(e.value)
+    # nrReconNeighbors > available views: zero pixels, no error
+    s4 = golden_scene("T0")
+    g4 = dmrecon.Scene.from_synth(s4, views=[0, 1, 2])
+    maps, st = g4.reconstruct(ok, [0])
+    assert int(st.n_filled) == 0 and not (maps[0]["depth"] > 0).any()
+
+
+def test_cancel():
+    """Progress::cancelled is polled once per frontier round (dmrecon.cc:353) -> B200MVS_ERR_CANCELLED."""
+    from mve_b200 import dmrecon
+    s = golden_scene("T0")
+    g = dmrecon.Scene.from_synth(s)
+    st = dmrecon.Settings()
+    prog = (dmrecon.Progress * 1)()
+    prog[0].cancelled = 1
+    refs = np.asarray([0], np.int32)
+    rc = g._lib.b200mvs_reconstruct(g._h, C.byref(st), 1, refs.ctypes.data_as(C.c_void_p), None, prog, None, None)
+    assert rc == -4
+    assert prog[0].status == 5
+
+
+def test_image_channel_variants():
+    """Grey and RGBA inputs are expanded / stripped like image_pyramid.cc:65-73."""
+    from mve_b200 import dmrecon
+    s = golden_scene("T0")
+    g = dmrecon.Scene(2)
+    grey = s.images[0][:, :, 1]
+    rgba = np.concatenate([s.images[0], np.full(s.images[0].shape[:2] + (1,), 7, np.uint8)], -1)
+    g.set_view(0, grey, s.flen[0], s.paspect[0], s.ppoint[0], s.rot[0], s.trans[0])
+    g.set_view(1, rgba, s.flen[0], s.paspect[0], s.ppoint[0], s.rot[0], s.trans[0])
+    assert (g.level(0, 0) == np.repeat(grey[:, :, None], 3, 2)).all()
+    assert (g.level(1, 0) == s.images[0]).all()
