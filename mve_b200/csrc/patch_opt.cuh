@@ -6,10 +6,18 @@
 // is the line-by-line behavioural spec.  Differences in STRUCTURE (not in results):
 //   * the colour-only sample set (computeNeighColorSamples) and the colour+derivative sample set
 //     (fastColAndDeriv) of one view at one patch state use identical bilinear formulas
-//     (mvs_tools.cc:119-128 vs :188-197), so a single fused sample set per (state, view) is drawn and
-//     kept in registers until the state changes (PatchSampler::update, patch_sampler.cc:259-271);
-//   * sums over the 25 samples are warp-shuffle reductions; the 3x3 normal equations are accumulated
-//     per lane in fp64 from fp32 products exactly as patch_optimization.cc:326-343 and reduced once.
+//     (mvs_tools.cc:119-128 vs :188-197), so ONE fused sample set per (state, view) is drawn;
+//   * the optimisation is organised as one PASS per patch state (depth, dzI, dzJ): a loop over the
+//     selected views that draws the fused sample set and immediately reduces it to what the reference
+//     reads at that state - NCC of the view (getFastNCC), the colour-scale update when one is due
+//     (computeColorScale), and the Gauss-Newton terms of the next step (optimizeDepthOnly /
+//     optimizeDepthAndNormal).  Nothing per-sample survives a pass, so the loop body exists once in
+//     the instruction stream (the first version inlined 16 copies and stalled on instruction fetch,
+//     profiles/r1_notes.md);
+//   * small per-view arrays (selected slots, colour scales, NCCs) live one element per lane and are
+//     read with warp shuffles; sums over the 25 samples are warp-shuffle reductions; the 3x3 normal
+//     equations are accumulated per lane in fp64 from fp32 products exactly as
+//     patch_optimization.cc:326-343 and reduced once per pass.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -94,6 +102,7 @@ struct Patch {
     const ViewParams* views;
     const ViewParams* rv;
     const float* lut;          // srgb2lin in shared memory (mvs_tools.cc:21-95)
+    int lane;
     bool act;                  // lane < 25
     float fi, fj;              // sample offsets (patch_optimization.cc:56-64)
     // ---- per-lane sample state ----
@@ -109,15 +118,19 @@ struct Patch {
     float depth, dzI, dzJ;
     bool ref_ok;               // sampler->success[refViewNr]
     int nsel;
-    int sel[MAX_LOCAL];        // global slots, ascending
-    float cs[MAX_LOCAL][3];    // colorScale of the selected views
-    float cn[MAX_LOCAL][3];    // cached colour samples of this lane
-    float cd[MAX_LOCAL][3];    // cached derivative samples of this lane
-    unsigned valid, col_ok, der_ok;   // per selected position: cache filled / colour path ok / derivative path ok
     unsigned avail;            // LocalViewSelection::available over global slots
     int iter;
     bool opti, converged, lvs_ok;
     unsigned n_sets;
+    // ---- lane-distributed small arrays: lane k (< nsel) holds element k ----
+    int sel_l;                 // selected global slot (ascending over lanes)
+    float cs0_l, cs1_l, cs2_l; // colorScale of selected view k
+    float ncc_l;               // NCC of selected view k at the state of the last pass
+    // ---- results of the last pass (valid for the current state and selected set) ----
+    unsigned p_col_ok, p_der_ok;   // bit k: colour / derivative path of selected view k succeeded
+    float p_num, p_den;            // optimizeDepthOnly sums
+    double pA0, pA1, pA2, pA3, pA4, pA5, pB0, pB1, pB2;   // optimizeDepthAndNormal sums
+    bool p_has_normal;
 
     // single_view.h:188-195 (K has the sparsity of camera.cc:125-144)
     __device__ __forceinline__ void project(const ViewParams* V, const LevelParams& L, float X, float Y, float Z,
@@ -147,12 +160,12 @@ struct Patch {
     }
 
     // PatchSampler ctor (patch_sampler.cc:19-62) + computeMasterSamples (:298-345)
-    __device__ __forceinline__ void init_sampler(int lane, int x, int y)
+    __device__ __forceinline__ void init_sampler(int x, int y)
     {
         act = lane < NS;
         const int di = act ? (lane % 5) - 2 : 0, dj = act ? (lane / 5) - 2 : 0;
         fi = (float)di; fj = (float)dj;
-        ref_ok = false; mm = 0.f; sqrDevX = 0.f; valid = col_ok = der_ok = 0u; n_sets = 0u;
+        ref_ok = false; mm = 0.f; sqrDevX = 0.f; n_sets = 0u;
         rx = ry = rz = px = py = pz = 0.f; m0 = m1 = m2 = e0 = e1 = e2 = 0.f;
         crx = cry = crz = cpx = cpy = cpz = mfp = 0.f;
         if (x - 2 < 0 || y - 2 < 0 || x + 2 > job->W - 1 || y + 2 > job->H - 1) return;
@@ -189,7 +202,6 @@ struct Patch {
     {
         ref_ok = true;
         compute_points();
-        valid = col_ok = der_ok = 0u;
     }
 
     // One fused sample set in view V at the current state: fastColAndDeriv (patch_sampler.cc:65-133 +
@@ -228,29 +240,30 @@ struct Patch {
         project(V, L, px, py, pz, qx, qy);
         const bool inb = qx > 0.f && qx < (float)(L.w - 1) && qy > 0.f && qy < (float)(L.h - 1);
         if (!__all_sync(FULL, inb || !act)) return 0u;
-        if (!act) return dok ? 3u : 1u;
-        float gx = 0.f, gy = 0.f;
-        if (dok) {
-            float tx, ty;
-            project(V, L, px + rx * step, py + ry * step, pz + rz * step, tx, ty);
-            gx = tx - qx; gy = ty - qy;
-        }
-        const int left = (int)floorf(qx), top = (int)floorf(qy);
-        const float fx = qx - (float)left, fy = qy - (float)top;
-        const uchar4* r0 = L.img + (size_t)top * L.pitch + left;
-        const uchar4* r1 = r0 + L.pitch;
-        const uchar4 A = __ldg(r0), B = __ldg(r0 + 1), C = __ldg(r1), D = __ldg(r1 + 1);
-        const float a[3] = {lut[A.x], lut[A.y], lut[A.z]};
-        const float b[3] = {lut[B.x], lut[B.y], lut[B.z]};
-        const float c[3] = {lut[C.x], lut[C.y], lut[C.z]};
-        const float e[3] = {lut[D.x], lut[D.y], lut[D.z]};
+        if (act) {
+            float gx = 0.f, gy = 0.f;
+            if (dok) {
+                float tx, ty;
+                project(V, L, px + rx * step, py + ry * step, pz + rz * step, tx, ty);
+                gx = tx - qx; gy = ty - qy;
+            }
+            const int left = (int)floorf(qx), top = (int)floorf(qy);
+            const float fx = qx - (float)left, fy = qy - (float)top;
+            const uchar4* r0 = L.img + (size_t)top * L.pitch + left;
+            const uchar4* r1 = r0 + L.pitch;
+            const uchar4 A = __ldg(r0), B = __ldg(r0 + 1), C = __ldg(r1), D = __ldg(r1 + 1);
+            const float a[3] = {lut[A.x], lut[A.y], lut[A.z]};
+            const float b[3] = {lut[B.x], lut[B.y], lut[B.z]};
+            const float c[3] = {lut[C.x], lut[C.y], lut[C.z]};
+            const float e[3] = {lut[D.x], lut[D.y], lut[D.z]};
 #pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
-            const float x0 = (1.f - fx) * a[ch] + fx * b[ch];
-            const float x3 = (1.f - fx) * c[ch] + fx * e[ch];
-            n[ch] = (1.f - fy) * x0 + fy * x3;
-            const float der = gx * (b[ch] - a[ch]) + gy * (c[ch] - a[ch]) + (gy * fx + gx * fy) * (a[ch] - b[ch] - c[ch] + e[ch]);
-            d[ch] = dok ? der / step : 0.f;
+            for (int ch = 0; ch < 3; ++ch) {
+                const float x0 = (1.f - fx) * a[ch] + fx * b[ch];
+                const float x3 = (1.f - fx) * c[ch] + fx * e[ch];
+                n[ch] = (1.f - fy) * x0 + fy * x3;
+                const float der = gx * (b[ch] - a[ch]) + gy * (c[ch] - a[ch]) + (gy * fx + gx * fy) * (a[ch] - b[ch] - c[ch] + e[ch]);
+                d[ch] = dok ? der / step : 0.f;
+            }
         }
         return dok ? 3u : 1u;
     }
@@ -266,114 +279,102 @@ struct Patch {
         return tmp > 0.f ? devXY / tmp : -1.f;
     }
 
-    template <int K> __device__ __forceinline__ void ensure()
+    // One pass over the selected views at the current state (see the header comment).
+    //   cs_pending : a computeColorScale() is due at this state (patch_optimization.cc:77,198,230)
+    //   want_ncc   : the NCCs of this state are read by the reference (getFastNCC, patch_optimization.cc:192,213,126)
+    //   want_normal: the next Gauss-Newton step is optimizeDepthAndNormal (else optimizeDepthOnly)
+    __device__ __noinline__ void pass(bool cs_pending, bool want_ncc, bool want_normal)
     {
-        if (valid & (1u << K)) return;
-        const unsigned r = sample(&views[job->gview[sel[K]]], cn[K], cd[K]);
-        valid |= 1u << K;
-        if (r & 1u) col_ok |= 1u << K;
-        if (r & 2u) der_ok |= 1u << K;
-    }
-    template <int K> __device__ __forceinline__ float ncc_sel()
-    {
-        ensure<K>();
-        if (!(col_ok & (1u << K))) return -1.f;
-        return ncc_of(cn[K]);
-    }
-
-    // patch_optimization.cc:81-111
-    template <int K> __device__ __forceinline__ bool color_scale_one()
-    {
-        ensure<K>();
-        if (!(col_ok & (1u << K))) return false;    // `return`, not `continue` (patch_optimization.cc:92-93)
-#pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
-            const float mc = ch == 0 ? m0 : (ch == 1 ? m1 : m2);
-            const float nn = cn[K][ch];
-            const float ab = warp_sum((mc - nn * cs[K][ch]) * nn);
-            const float aa = warp_sum(nn * nn);
-            if ((double)fabsf(aa) > 1e-6) {
-                cs[K][ch] += ab / aa;
-                if ((double)cs[K][ch] > 1e3) opti = false;
-            } else
-                opti = false;
-        }
-        return true;
-    }
-    __device__ __forceinline__ void color_scale()
-    {
-        if (!st->use_color_scale) return;
-        if (nsel > 0 && !color_scale_one<0>()) return;
-        if (nsel > 1 && !color_scale_one<1>()) return;
-        if (nsel > 2 && !color_scale_one<2>()) return;
-        if (nsel > 3 && !color_scale_one<3>()) return;
-    }
-
-    // patch_optimization.cc:265-299
-    template <int K> __device__ __forceinline__ bool depth_acc(float& num, float& den)
-    {
-        ensure<K>();
-        if (!(der_ok & (1u << K))) return false;
-        const float c0 = cs[K][0] * cd[K][0], c1 = cs[K][1] * cd[K][1], c2 = cs[K][2] * cd[K][2];
-        const float r0 = m0 - cs[K][0] * cn[K][0], r1 = m1 - cs[K][1] * cn[K][1], r2 = m2 - cs[K][2] * cn[K][2];
-        num += c0 * r0 + c1 * r1 + c2 * r2;
-        den += c0 * c0 + c1 * c1 + c2 * c2;
-        return true;
-    }
-    __device__ __forceinline__ void depth_step()
-    {
+        p_col_ok = p_der_ok = 0u;
         float num = 0.f, den = 0.f;
-        bool ok = true;
-        if (ok && nsel > 0) ok = depth_acc<0>(num, den);
-        if (ok && nsel > 1) ok = depth_acc<1>(num, den);
-        if (ok && nsel > 2) ok = depth_acc<2>(num, den);
-        if (ok && nsel > 3) ok = depth_acc<3>(num, den);
-        if (!ok) { opti = false; return; }
-        if (!act) { num = 0.f; den = 0.f; }
-        num = warp_sum(num); den = warp_sum(den);
-        if (den > 0.f) {
-            depth += num / den;
+        double A0 = 0, A1 = 0, A2 = 0, A3 = 0, A4 = 0, A5 = 0, B0 = 0, B1 = 0, B2 = 0;
+        bool cs_active = cs_pending && st->use_color_scale;
+        for (int k = 0; k < nsel; ++k) {
+            const int slot = __shfl_sync(FULL, sel_l, k);
+            float n[3], d[3];
+            const unsigned r = sample(&views[job->gview[slot]], n, d);
+            if (r & 1u) p_col_ok |= 1u << k;
+            if (r & 2u) p_der_ok |= 1u << k;
+            if (want_ncc) {
+                const float v = (r & 1u) ? ncc_of(n) : -1.f;
+                if (lane == k) ncc_l = v;
+            }
+            float c0 = __shfl_sync(FULL, cs0_l, k), c1 = __shfl_sync(FULL, cs1_l, k), c2 = __shfl_sync(FULL, cs2_l, k);
+            // computeColorScale for this view (patch_optimization.cc:88-110); a failed view ends the whole
+            // update (`return`, not `continue`, :92-93)
+            if (cs_active) {
+                if (!(r & 1u)) cs_active = false;
+                else {
+                    float cc[3] = {c0, c1, c2};
+#pragma unroll
+                    for (int ch = 0; ch < 3; ++ch) {
+                        const float mc = ch == 0 ? m0 : (ch == 1 ? m1 : m2);
+                        const float ab = warp_sum((mc - n[ch] * cc[ch]) * n[ch]);
+                        const float aa = warp_sum(n[ch] * n[ch]);
+                        if ((double)fabsf(aa) > 1e-6) {
+                            cc[ch] += ab / aa;
+                            if ((double)cc[ch] > 1e3) opti = false;
+                        } else
+                            opti = false;
+                    }
+                    c0 = cc[0]; c1 = cc[1]; c2 = cc[2];
+                    if (lane == k) { cs0_l = c0; cs1_l = c1; cs2_l = c2; }
+                }
+            }
+            // Gauss-Newton terms (patch_optimization.cc:283-288 / :324-343); only meaningful when every view's
+            // derivative path succeeded, which the caller checks through p_der_ok
+            if ((r & 2u) && act) {
+                const float g0 = c0 * d[0], g1 = c1 * d[1], g2 = c2 * d[2];
+                const float r0 = m0 - c0 * n[0], r1 = m1 - c1 * n[1], r2 = m2 - c2 * n[2];
+                num += g0 * r0 + g1 * r1 + g2 * r2;
+                den += g0 * g0 + g1 * g1 + g2 * g2;
+                if (want_normal) {
+                    const float gg[3] = {g0, g1, g2};
+                    const float rr[3] = {r0, r1, r2};
+#pragma unroll
+                    for (int ch = 0; ch < 3; ++ch) {
+                        const float a0 = gg[ch];
+                        const float a1 = fi * a0;      // (ii * cs) * deriv == ii * (cs * deriv) exactly for ii in {-2..2}
+                        const float a2 = fj * a0;
+                        A0 += (double)(a0 * a0); A1 += (double)(a0 * a1); A2 += (double)(a0 * a2);
+                        A3 += (double)(a1 * a1); A4 += (double)(a1 * a2); A5 += (double)(a2 * a2);
+                        B0 += (double)(a0 * rr[ch]); B1 += (double)(a1 * rr[ch]); B2 += (double)(a2 * rr[ch]);
+                    }
+                }
+            }
+        }
+        p_num = warp_sum(num);
+        p_den = warp_sum(den);
+        p_has_normal = want_normal;
+        if (want_normal) {
+            pA0 = warp_sum(A0); pA1 = warp_sum(A1); pA2 = warp_sum(A2); pA3 = warp_sum(A3); pA4 = warp_sum(A4); pA5 = warp_sum(A5);
+            pB0 = warp_sum(B0); pB1 = warp_sum(B1); pB2 = warp_sum(B2);
+        }
+    }
+
+    __device__ __forceinline__ bool all_der_ok() const { return p_der_ok == ((1u << nsel) - 1u); }
+
+    // optimizeDepthOnly (patch_optimization.cc:265-299) from the sums of the last pass. Returns true when the state moved.
+    __device__ __forceinline__ bool depth_step()
+    {
+        if (!all_der_ok()) { opti = false; return false; }
+        if (p_den > 0.f) {
+            depth += p_num / p_den;
             update();
             opti = ref_ok;
+            return true;
         }
+        return false;
     }
 
-    // patch_optimization.cc:302-364 with matrix_tools.h:392-398,460-475
-    template <int K> __device__ __forceinline__ bool normal_acc(double (&A)[6], double (&B)[3])
+    // optimizeDepthAndNormal (patch_optimization.cc:302-364, matrix_tools.h:392-398,460-475) from the last pass.
+    __device__ __forceinline__ bool normal_step()
     {
-        ensure<K>();
-        if (!(der_ok & (1u << K))) return false;
-#pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
-            const float mc = ch == 0 ? m0 : (ch == 1 ? m1 : m2);
-            const float a0 = cs[K][ch] * cd[K][ch];
-            const float a1 = fi * cs[K][ch] * cd[K][ch];
-            const float a2 = fj * cs[K][ch] * cd[K][ch];
-            const float b = mc - cs[K][ch] * cn[K][ch];
-            A[0] += (double)(a0 * a0); A[1] += (double)(a0 * a1); A[2] += (double)(a0 * a2);
-            A[3] += (double)(a1 * a1); A[4] += (double)(a1 * a2); A[5] += (double)(a2 * a2);
-            B[0] += (double)(a0 * b); B[1] += (double)(a1 * b); B[2] += (double)(a2 * b);
-        }
-        return true;
-    }
-    __device__ __forceinline__ void normal_step()
-    {
-        if (!lvs_ok) return;
-        double A[6] = {0, 0, 0, 0, 0, 0}, B[3] = {0, 0, 0};
-        bool ok = true;
-        if (ok && nsel > 0) ok = normal_acc<0>(A, B);
-        if (ok && nsel > 1) ok = normal_acc<1>(A, B);
-        if (ok && nsel > 2) ok = normal_acc<2>(A, B);
-        if (ok && nsel > 3) ok = normal_acc<3>(A, B);
-        if (!ok) { opti = false; return; }
-#pragma unroll
-        for (int q = 0; q < 6; ++q) A[q] = warp_sum(act ? A[q] : 0.0);
-#pragma unroll
-        for (int q = 0; q < 3; ++q) B[q] = warp_sum(act ? B[q] : 0.0);
-        const double m[9] = {A[0], A[1], A[2], A[1], A[3], A[4], A[2], A[4], A[5]};
+        if (!all_der_ok()) { opti = false; return false; }
+        const double m[9] = {pA0, pA1, pA2, pA1, pA3, pA4, pA2, pA4, pA5};
         const double det = m[0] * m[4] * m[8] + m[1] * m[5] * m[6] + m[2] * m[3] * m[7]
                          - m[2] * m[4] * m[6] - m[1] * m[3] * m[8] - m[0] * m[5] * m[7];
-        if (det == 0.0) { opti = false; return; }
+        if (det == 0.0) { opti = false; return false; }
         double inv[9];
         inv[0] = m[4] * m[8] - m[5] * m[7];
         inv[1] = m[2] * m[7] - m[1] * m[8];
@@ -386,48 +387,42 @@ struct Patch {
         inv[8] = m[0] * m[4] - m[1] * m[3];
 #pragma unroll
         for (int q = 0; q < 9; ++q) inv[q] /= det;
-        const float X0 = (float)(inv[0] * B[0] + inv[1] * B[1] + inv[2] * B[2]);
-        const float X1 = (float)(inv[3] * B[0] + inv[4] * B[1] + inv[5] * B[2]);
-        const float X2 = (float)(inv[6] * B[0] + inv[7] * B[1] + inv[8] * B[2]);
+        const float X0 = (float)(inv[0] * pB0 + inv[1] * pB1 + inv[2] * pB2);
+        const float X1 = (float)(inv[3] * pB0 + inv[4] * pB1 + inv[5] * pB2);
+        const float X2 = (float)(inv[6] * pB0 + inv[7] * pB1 + inv[8] * pB2);
         dzI += X1; dzJ += X2; depth += X0;
         update();
         opti = ref_ok;
+        return true;
     }
 
-    // ---- sorted insert / erase on the selected set (std::set semantics), compile-time indices only ----
-    __device__ __forceinline__ void sel_erase_mask(unsigned mask)
+    // ---- sorted insert / erase on the lane-distributed selected set (std::set semantics) ----
+    __device__ __forceinline__ void sel_erase_mask(unsigned mask)       // bit k: remove element k
     {
-#pragma unroll
-        for (int k = MAX_LOCAL - 1; k >= 0; --k) {
-            if ((mask >> k) & 1u) {
-#pragma unroll
-                for (int q = k; q < MAX_LOCAL - 1; ++q) {
-                    sel[q] = sel[q + 1];
-                    cs[q][0] = cs[q + 1][0]; cs[q][1] = cs[q + 1][1]; cs[q][2] = cs[q + 1][2];
-                }
-                --nsel;
-            }
+        // gather: new position p takes the p-th kept element
+        int src = 0, cnt = 0;
+        for (int k = 0; k < MAX_LOCAL; ++k) {
+            const bool kk = k < nsel && !((mask >> k) & 1u);
+            if (kk) { if (cnt == lane) src = k; ++cnt; }
         }
-        valid = col_ok = der_ok = 0u;
+        const int s = __shfl_sync(FULL, sel_l, src);
+        const float a = __shfl_sync(FULL, cs0_l, src), b = __shfl_sync(FULL, cs1_l, src), c = __shfl_sync(FULL, cs2_l, src);
+        const float v = __shfl_sync(FULL, ncc_l, src);
+        nsel = cnt;
+        if (lane < cnt) { sel_l = s; cs0_l = a; cs1_l = b; cs2_l = c; ncc_l = v; }
+        else { sel_l = 0xFF; }
     }
     __device__ __forceinline__ void sel_insert(int slot, float cs_init)
     {
-        int pos = 0;
-#pragma unroll
-        for (int k = 0; k < MAX_LOCAL; ++k) if (k < nsel && sel[k] < slot) ++pos;
-#pragma unroll
-        for (int q = MAX_LOCAL - 1; q >= 1; --q) {
-            if (q > pos) {
-                sel[q] = sel[q - 1];
-                cs[q][0] = cs[q - 1][0]; cs[q][1] = cs[q - 1][1]; cs[q][2] = cs[q - 1][2];
-            }
-        }
-#pragma unroll
-        for (int q = 0; q < MAX_LOCAL; ++q) {
-            if (q == pos) { sel[q] = slot; cs[q][0] = cs[q][1] = cs[q][2] = cs_init; }
-        }
+        // position = number of selected slots smaller than `slot`
+        const unsigned smaller = __ballot_sync(FULL, lane < nsel && sel_l < slot);
+        const int pos = __popc(smaller);
+        const int s_up = __shfl_up_sync(FULL, sel_l, 1);
+        const float a_up = __shfl_up_sync(FULL, cs0_l, 1), b_up = __shfl_up_sync(FULL, cs1_l, 1), c_up = __shfl_up_sync(FULL, cs2_l, 1);
+        const float v_up = __shfl_up_sync(FULL, ncc_l, 1);
+        if (lane > pos && lane <= nsel) { sel_l = s_up; cs0_l = a_up; cs1_l = b_up; cs2_l = c_up; ncc_l = v_up; }
+        if (lane == pos) { sel_l = slot; cs0_l = cs1_l = cs2_l = cs_init; ncc_l = 0.f; }
         ++nsel;
-        valid = col_ok = der_ok = 0u;
     }
 
     // mvs_tools.h:56-69
@@ -442,10 +437,11 @@ struct Patch {
     static __device__ __forceinline__ float deg_acos(float dp) { return acosf(dp) * 180.f / 3.141592653589793f; }
 
     // LocalViewSelection::performVS (local_view_selection.cc:57-147); lane i evaluates candidate slot i.
-    __device__ __forceinline__ void lvs_perform(int lane, float cs_init)
+    __device__ __noinline__ void lvs_perform()
     {
         const unsigned N = st->nr_recon_neighbors;
         if ((unsigned)nsel == N) { lvs_ok = true; return; }
+        const float cs_init = 1.f / mm;
         // refDir
         float rdx = cpx - __ldg(&rv->campos[0]), rdy = cpy - __ldg(&rv->campos[1]), rdz = cpz - __ldg(&rv->campos[2]);
         {
@@ -479,36 +475,34 @@ struct Patch {
         bool found = true;
         while ((unsigned)nsel < N && found) {
             found = false;
+            const bool mine = lane < G && ((avail >> lane) & 1u);
             float score = -1.f;
-            if (lane < G && ((avail >> lane) & 1u)) {
+            if (mine) {
                 score = my_ncc;
                 if (mfp / nfp < 0.5f) score *= 0.01f;
                 float dp = clamp1(rdx * vdx + rdy * vdy + rdz * vdz);
                 score *= plx_weight(deg_acos(dp));
             }
             // parallax / epipolar terms against every already selected view (geometry broadcast from its lane)
-#pragma unroll
-            for (int k = 0; k < MAX_LOCAL; ++k) {
-                if (k < nsel) {
-                    const int s = sel[k];
-                    const float sx = __shfl_sync(FULL, vdx, s), sy = __shfl_sync(FULL, vdy, s), sz = __shfl_sync(FULL, vdz, s);
-                    const float ex = __shfl_sync(FULL, epx, s), ey = __shfl_sync(FULL, epy, s), ez = __shfl_sync(FULL, epz, s);
-                    if (lane < G && ((avail >> lane) & 1u)) {
-                        float dp = clamp1(sx * vdx + sy * vdy + sz * vdz);
-                        score *= plx_weight(deg_acos(dp));
-                        dp = clamp1(epx * ex + epy * ey + epz * ez);
-                        float angle = fabsf(deg_acos(dp));
-                        if (angle > 90.f) angle = 180.f - angle;
-                        angle = fmaxf(angle, 1.f);
-                        if (angle < st->min_parallax) score *= angle / st->min_parallax;
-                    }
+            for (int k = 0; k < nsel; ++k) {
+                const int s = __shfl_sync(FULL, sel_l, k);
+                const float sx = __shfl_sync(FULL, vdx, s), sy = __shfl_sync(FULL, vdy, s), sz = __shfl_sync(FULL, vdz, s);
+                const float ex = __shfl_sync(FULL, epx, s), ey = __shfl_sync(FULL, epy, s), ez = __shfl_sync(FULL, epz, s);
+                if (mine) {
+                    float dp = clamp1(sx * vdx + sy * vdy + sz * vdz);
+                    score *= plx_weight(deg_acos(dp));
+                    dp = clamp1(epx * ex + epy * ey + epz * ez);
+                    float angle = fabsf(deg_acos(dp));
+                    if (angle > 90.f) angle = 180.f - angle;
+                    angle = fmaxf(angle, 1.f);
+                    if (angle < st->min_parallax) score *= angle / st->min_parallax;
                 }
             }
-            const bool cand = lane < G && ((avail >> lane) & 1u) && (score > 0.f);   // NaN compares false, like `score > maxScore`
+            const bool cand = mine && (score > 0.f);       // NaN compares false, like `score > maxScore`
             const float best = warp_max(cand ? score : -1.f);
             const unsigned winners = __ballot_sync(FULL, cand && score == best);
             if (best > 0.f && winners) {
-                const int w = __ffs(winners) - 1;        // strict '>' in index order: lowest index wins ties
+                const int w = __ffs(winners) - 1;           // strict '>' in index order: lowest index wins ties
                 found = true;
                 sel_insert(w, cs_init);
                 avail &= ~(1u << w);
@@ -518,83 +512,80 @@ struct Patch {
     }
 
     // PatchOptimization ctor (patch_optimization.cc:21-78) incl. LocalViewSelection ctor (local_view_selection.cc:19-54)
-    __device__ __forceinline__ void init(int lane, const PatchIn& in)
+    __device__ __forceinline__ void init(const PatchIn& in)
     {
         rv = &views[job->ref_view];
         depth = in.depth; dzI = in.dzI; dzJ = in.dzJ;
         iter = 0; opti = true; converged = false; lvs_ok = false;
         nsel = 0; avail = 0u;
-#pragma unroll
-        for (int k = 0; k < MAX_LOCAL; ++k) {
-            sel[k] = 0xFF; cs[k][0] = cs[k][1] = cs[k][2] = 0.f;
-            cn[k][0] = cn[k][1] = cn[k][2] = 0.f; cd[k][0] = cd[k][1] = cd[k][2] = 0.f;
-        }
-        init_sampler(lane, in.x, in.y);
-        // propagated ids arrive ascending
-#pragma unroll
-        for (int k = 0; k < MAX_LOCAL; ++k) {
-            const int s = (in.slots >> (8 * k)) & 0xFF;
-            if (s != 0xFF) { sel[k] = s; nsel = k + 1; }
-        }
+        sel_l = 0xFF; cs0_l = cs1_l = cs2_l = 0.f; ncc_l = 0.f;
+        p_col_ok = p_der_ok = 0u; p_num = p_den = 0.f; p_has_normal = false;
+        pA0 = pA1 = pA2 = pA3 = pA4 = pA5 = pB0 = pB1 = pB2 = 0.0;
+        init_sampler(in.x, in.y);
+        // propagated ids arrive ascending, 0xFF padded
+        if (lane < MAX_LOCAL) sel_l = (in.slots >> (8 * lane)) & 0xFF;
+        nsel = __popc(__ballot_sync(FULL, lane < MAX_LOCAL && sel_l != 0xFF));
         if (!ref_ok) { opti = false; return; }
         const unsigned N = st->nr_recon_neighbors;
         if ((unsigned)nsel == N) lvs_ok = true;
-        else if ((unsigned)nsel > N) nsel = 0;
+        else if ((unsigned)nsel > N) { nsel = 0; sel_l = 0xFF; }
         avail = job->n_global >= 32 ? FULL : ((1u << job->n_global) - 1u);
-#pragma unroll
-        for (int k = 0; k < MAX_LOCAL; ++k) if (k < nsel) avail &= ~(1u << sel[k]);
+        {
+            unsigned m = 0u;
+            for (int k = 0; k < nsel; ++k) m |= 1u << __shfl_sync(FULL, sel_l, k);
+            avail &= ~m;
+        }
         const float cs_init = 1.f / mm;
-#pragma unroll
-        for (int k = 0; k < MAX_LOCAL; ++k) cs[k][0] = cs[k][1] = cs[k][2] = cs_init;
-        lvs_perform(lane, cs_init);
+        cs0_l = cs1_l = cs2_l = cs_init;
+        lvs_perform();
         if (!lvs_ok) { opti = false; return; }
-        color_scale();
     }
 
-    __device__ __forceinline__ float ncc_at(int k)
-    {
-        switch (k) { case 0: return ncc_sel<0>(); case 1: return ncc_sel<1>(); case 2: return ncc_sel<2>(); default: return ncc_sel<3>(); }
-    }
-
-    // PatchOptimization::doAutoOptimization (patch_optimization.cc:170-242)
-    __device__ __forceinline__ void auto_optimize(int lane)
+    // PatchOptimization::doAutoOptimization (patch_optimization.cc:170-242) on top of passes.
+    __device__ __forceinline__ void auto_optimize()
     {
         if (!lvs_ok || !opti) return;
-        while (iter < 4 && opti) { depth_step(); ++iter; }
+        // ctor's computeColorScale() at the initial state + the terms of the first depth step
+        pass(true, false, false);
+        if (!opti) return;
+        // first four iterations only refine depth (:177-180)
+        while (iter < 4 && opti) {
+            const bool moved = depth_step();
+            ++iter;
+            if (moved && opti) pass(false, iter == 4, iter == 4);
+        }
         bool viewRemoved = false;
         while ((unsigned)iter < st->max_iterations && lvs_ok && opti) {
-            float oldN[MAX_LOCAL];
-            const int n_old = nsel;
-#pragma unroll
-            for (int k = 0; k < MAX_LOCAL; ++k) oldN[k] = (k < n_old) ? ncc_at(k) : 0.f;
-            opti = false;
-            if (iter % 5 == 4 || viewRemoved) {
-                normal_step();
-                color_scale();
-                viewRemoved = false;
-            } else
-                depth_step();
-            if (!opti) return;
-            bool conv = true;
-            unsigned tbr = 0u;
-#pragma unroll
-            for (int k = 0; k < MAX_LOCAL; ++k) {
-                if (k < n_old) {
-                    const float v = ncc_at(k);
-                    const float df = fabsf(v - oldN[k]);
-                    if (df > st->min_refine_diff) conv = false;
-                    if (v < st->accept_ncc || (iter == 14 && df > st->min_refine_diff)) { tbr |= 1u << k; viewRemoved = true; }
-                }
+            // oldNCC (:190-193): NCCs of the current state.  They are in ncc_l unless the state did not move since a
+            // pass without NCCs (only possible when a depth step had denom <= 0).
+            const bool normal = (iter % 5 == 4) || viewRemoved;
+            if ((normal && !p_has_normal) || iter == 4) {
+                // (re)draw the current state with everything this iteration reads
+                if (!(iter == 4 && p_has_normal)) pass(false, true, normal);
             }
-            if (viewRemoved) {
+            const float old = ncc_l;
+            opti = false;
+            bool moved;
+            if (normal) { moved = normal_step(); viewRemoved = false; }
+            else moved = depth_step();
+            if (!opti) return;
+            (void)moved;
+            // new state: NCCs, the colour-scale update that follows a depth+normal step (:198), next step's terms
+            const bool next_normal = ((iter + 1) % 5 == 4);
+            pass(normal, true, next_normal);
+            if (!opti) return;
+            const float df = fabsf(ncc_l - old);
+            const bool mine = lane < nsel;
+            const bool conv = !__any_sync(FULL, mine && df > st->min_refine_diff);
+            const unsigned tbr = __ballot_sync(FULL, mine && (ncc_l < st->accept_ncc || (iter == 14 && df > st->min_refine_diff)));
+            if (tbr) {
+                viewRemoved = true;
                 // LocalViewSelection::replaceViews (local_view_selection.cc:150-160)
                 sel_erase_mask(tbr);
                 lvs_ok = false;
-                lvs_perform(lane, 1.f / mm);
+                lvs_perform();
                 if (!lvs_ok) return;
-                color_scale();
-            } else if (!opti) {
-                return;
+                pass(true, true, true);                    // computeColorScale() of :230 on the new set (+ next terms)
             } else if (conv) {
                 converged = true;
                 return;
@@ -611,13 +602,16 @@ struct Patch {
         out.flags = (converged ? 1 : 0) | (opti ? 2 : 0);
         unsigned s = 0u;
 #pragma unroll
-        for (int k = 0; k < MAX_LOCAL; ++k) s |= (unsigned)((k < nsel) ? (sel[k] & 0xFF) : 0xFF) << (8 * k);
+        for (int k = 0; k < MAX_LOCAL; ++k) {
+            const int v = __shfl_sync(FULL, sel_l, k);
+            s |= (unsigned)((k < nsel) ? (v & 0xFF) : 0xFF) << (8 * k);
+        }
         out.slots = s;
         out.conf = 0.f; out.nx = out.ny = out.nz = 0.f;
         if (!converged) return;
+        // mean NCC of the final state (the NCCs of the last pass)
         float mean = 0.f;
-#pragma unroll
-        for (int k = 0; k < MAX_LOCAL; ++k) if (k < nsel) mean += ncc_at(k);
+        for (int k = 0; k < nsel; ++k) mean += __shfl_sync(FULL, ncc_l, k);
         mean /= (float)nsel;
         const float score = (mean - st->accept_ncc) / (1.f - st->accept_ncc);
         const float ax_ = __shfl_sync(FULL, px, CENTER + 2) - __shfl_sync(FULL, px, CENTER - 2);
@@ -640,9 +634,9 @@ __device__ __forceinline__ unsigned optimize_patch(const DevSettings* st, const 
                                                    const float* lut, int lane, const PatchIn& in, PatchOut& out)
 {
     Patch p;
-    p.st = st; p.job = job; p.views = views; p.lut = lut;
-    p.init(lane, in);
-    p.auto_optimize(lane);
+    p.st = st; p.job = job; p.views = views; p.lut = lut; p.lane = lane;
+    p.init(in);
+    p.auto_optimize();
     p.finish(out);
     return p.n_sets;
 }

@@ -221,7 +221,10 @@ class Scene:
             results = []
             for j, r in enumerate(refs):
                 w, h = C.c_int(), C.c_int()
-                self._check(self._lib.b200mvs_get_level(self._h, int(r), settings.scale, C.byref(w), C.byref(h), None))
+                if self._lib.b200mvs_get_level(self._h, int(r), settings.scale, C.byref(w), C.byref(h), None) != 0:
+                    # let b200mvs_reconstruct report it with the reference's own message (dmrecon.cc:37-75)
+                    maps_arr, results = None, None
+                    break
                 W, H = w.value, h.value
                 if out is not None:
                     d = out[j]
