@@ -11,6 +11,8 @@
 #include <ctime>
 #include <mutex>
 #include <string>
+#include <thread>
+#include <atomic>
 #include <vector>
 
 using namespace b200mvs;
@@ -326,9 +328,12 @@ __global__ void k_export_rgb(const uchar4* __restrict__ src, int w, int h, int p
 // kernels: patch optimisation + frontier
 // ------------------------------------------------------------------------------------------------
 constexpr int OPT_WARPS = 4;
+#ifndef OPT_MIN_BLOCKS
+#define OPT_MIN_BLOCKS 4     // registers per thread <= 65536 / (OPT_MIN_BLOCKS * 128); tuned on B200, profiles/r1_notes.md
+#endif
 
 // One warp per queue entry: PatchOptimization ctor + doAutoOptimization + computeConfidence.
-__global__ void __launch_bounds__(OPT_WARPS * 32)
+__global__ void __launch_bounds__(OPT_WARPS * 32, OPT_MIN_BLOCKS)
 k_optimize(const Entry* __restrict__ in, PatchOut* __restrict__ out, const unsigned long long* __restrict__ n_ptr, int n_max,
            const DevSettings* __restrict__ st, const JobParams* __restrict__ jobs, const ViewParams* __restrict__ views,
            const float* __restrict__ g_lut, unsigned long long* __restrict__ counters)
@@ -523,7 +528,6 @@ int upload_common(b200mvs_ctx* ctx, int id, const uint8_t* d_src, int w, int h, 
                   const float* pp, const float* rot, const float* trans, cudaStream_t stream)
 {
     HostView& v = ctx->views[id];
-    if (v.d_base) { cudaFree(v.d_base); v.d_base = nullptr; }
     v.valid = false;
     v.w = w; v.h = h; v.flen = flen; v.paspect = paspect; v.pp[0] = pp[0]; v.pp[1] = pp[1];
     std::memcpy(v.rot, rot, sizeof(v.rot));
@@ -554,8 +558,12 @@ int upload_common(b200mvs_ctx* ctx, int id, const uint8_t* d_src, int w, int h, 
     if ((int)v.lv.size() > MAX_LEVELS) return fail(ctx, B200MVS_ERR_UNSUPPORTED, "image too large: %d pyramid levels", (int)v.lv.size());
     size_t total = 0;
     for (HostLevel& L : v.lv) total += (size_t)L.pitch * L.h;
-    CK(cudaMalloc(&v.d_base, total * sizeof(uchar4)));
-    v.bytes = total * sizeof(uchar4);
+    if (!v.d_base || v.bytes != total * sizeof(uchar4)) {
+        if (v.d_base) { cudaFree(v.d_base); v.d_base = nullptr; }
+        CK(cudaMalloc(&v.d_base, total * sizeof(uchar4)));
+        v.bytes = total * sizeof(uchar4);
+        ctx->views_dirty = true;
+    }
     size_t off = 0;
     for (HostLevel& L : v.lv) { L.d_img = v.d_base + off; off += (size_t)L.pitch * L.h; }
     const dim3 blk(32, 8);
@@ -907,9 +915,29 @@ int b200mvs_reconstruct(b200mvs_ctx* ctx, const b200mvs_settings* s, int n_refs,
     std::vector<Entry> seeds;
     size_t total_px = 0;
     std::vector<size_t> px_off(n_refs);
+    // The per-view host work is independent (the reference runs whole DMRecons on OpenMP threads,
+    // apps/dmrecon/dmrecon.cc:285): spread it over host threads.
+    std::vector<std::vector<Seed>> seed_lists(n_refs);
+    {
+        std::atomic<int> next_job(0);
+        auto worker = [&]() {
+            for (;;) {
+                const int j = next_job.fetch_add(1);
+                if (j >= n_refs) break;
+                if (progress) { progress[j].status = 1; progress[j].start_time = (uint64_t)t_start; progress[j].filled = 0; progress[j].queue_size = 0; }
+                gsels[j] = global_view_selection(ctx, *s, refs[j]);
+                if (gsels[j].empty()) continue;
+                if (progress) progress[j].status = 2;
+                seed_lists[j] = collect_seeds(ctx, *s, refs[j], gsels[j]);
+            }
+        };
+        const int n_threads = std::max(1, std::min<int>(n_refs, (int)std::thread::hardware_concurrency()));
+        std::vector<std::thread> pool;
+        for (int t = 1; t < n_threads; ++t) pool.emplace_back(worker);
+        worker();
+        for (std::thread& t : pool) t.join();
+    }
     for (int j = 0; j < n_refs; ++j) {
-        if (progress) { progress[j].status = 1; progress[j].start_time = (uint64_t)t_start; progress[j].filled = 0; progress[j].queue_size = 0; }
-        gsels[j] = global_view_selection(ctx, *s, refs[j]);
         if (gsels[j].empty()) {
             if (failed_view) *failed_view = refs[j];
             return fail(ctx, B200MVS_ERR_GLOBAL_VS, "Global View Selection failed");
@@ -917,9 +945,7 @@ int b200mvs_reconstruct(b200mvs_ctx* ctx, const b200mvs_settings* s, int n_refs,
         if ((rc = make_job(ctx, *s, refs[j], gsels[j], jobs[j]))) return rc;
         px_off[j] = total_px;
         total_px += (size_t)jobs[j].W * jobs[j].H;
-        if (progress) progress[j].status = 2;
-        const std::vector<Seed> sd = collect_seeds(ctx, *s, refs[j], gsels[j]);
-        for (const Seed& q : sd) {
+        for (const Seed& q : seed_lists[j]) {
             Entry e;
             // a seed outside the image fails in the PatchSampler ctor (patch_sampler.cc:47-50); keep it so that the
             // processed count matches, the kernel rejects it by the same bounds test
@@ -929,7 +955,7 @@ int b200mvs_reconstruct(b200mvs_ctx* ctx, const b200mvs_settings* s, int n_refs,
             e.conf = 0.f; e.depth = q.depth; e.dzI = 0.f; e.dzJ = 0.f; e.slots = 0xFFFFFFFFu; e.pad = 0;
             seeds.push_back(e);
         }
-        if (stats) stats->n_seeds_processed += sd.size();
+        if (stats) stats->n_seeds_processed += seed_lists[j].size();
     }
 
     // ---- device buffers ----

@@ -130,17 +130,21 @@ struct Patch {
     unsigned p_col_ok, p_der_ok;   // bit k: colour / derivative path of selected view k succeeded
     float p_num, p_den;            // optimizeDepthOnly sums
     double pA0, pA1, pA2, pA3, pA4, pA5, pB0, pB1, pB2;   // optimizeDepthAndNormal sums
-    bool p_has_normal;
+    bool p_has_normal, p_has_ncc;
+    float cand_ncc_l;          // NCC of candidate global slot `lane` (local view selection)
 
-    // single_view.h:188-195 (K has the sparsity of camera.cc:125-144)
-    __device__ __forceinline__ void project(const ViewParams* V, const LevelParams& L, float X, float Y, float Z,
+    // single_view.h:188-195 (K has the sparsity of camera.cc:125-144).  x = (K cp).x / cp.z - 0.5 is evaluated with one
+    // correctly rounded reciprocal shared by x and y (<= 1 ulp from the reference's two divisions; measured effect on
+    // parity in tests/test_gpu_parity.py).
+    __device__ __forceinline__ void project(const float (&w)[12], const LevelParams& L, float X, float Y, float Z,
                                             float& x, float& y) const
     {
-        const float c0 = __ldg(&V->w2c[0]) * X + __ldg(&V->w2c[1]) * Y + __ldg(&V->w2c[2]) * Z + __ldg(&V->w2c[3]);
-        const float c1 = __ldg(&V->w2c[4]) * X + __ldg(&V->w2c[5]) * Y + __ldg(&V->w2c[6]) * Z + __ldg(&V->w2c[7]);
-        const float c2 = __ldg(&V->w2c[8]) * X + __ldg(&V->w2c[9]) * Y + __ldg(&V->w2c[10]) * Z + __ldg(&V->w2c[11]);
-        x = (L.ax * c0 + L.cx * c2) / c2 - 0.5f;
-        y = (L.ay * c1 + L.cy * c2) / c2 - 0.5f;
+        const float c0 = w[0] * X + w[1] * Y + w[2] * Z + w[3];
+        const float c1 = w[4] * X + w[5] * Y + w[6] * Z + w[7];
+        const float c2 = w[8] * X + w[9] * Y + w[10] * Z + w[11];
+        const float ic2 = __frcp_rn(c2);
+        x = (L.ax * c0 + L.cx * c2) * ic2 - 0.5f;
+        y = (L.ay * c1 + L.cy * c2) * ic2 - 0.5f;
     }
 
     // patch_sampler.cc:274-295 (+ the centre point / master footprint used by every sample set)
@@ -211,7 +215,15 @@ struct Patch {
     {
         ++n_sets;
         n[0] = n[1] = n[2] = 0.f; d[0] = d[1] = d[2] = 0.f;
-        const float nz = __ldg(&V->w2c[8]) * cpx + __ldg(&V->w2c[9]) * cpy + __ldg(&V->w2c[10]) * cpz + __ldg(&V->w2c[11]);
+        float w[12];
+        {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(&V->w2c[0]));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(&V->w2c[4]));
+            const float4 c = __ldg(reinterpret_cast<const float4*>(&V->w2c[8]));
+            w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+            w[8] = c.x; w[9] = c.y; w[10] = c.z; w[11] = c.w;
+        }
+        const float nz = w[8] * cpx + w[9] * cpy + w[10] * cpz + w[11];
         const float nfp = nz * __ldg(&V->inv_ax0);
         // mfp <= 0 makes the reference throw std::out_of_range (patch_sampler.cc:78-82); it cannot happen for
         // depth > 0 because the centre ray has positive camera z.  Treated as a failed view here.
@@ -228,23 +240,23 @@ struct Patch {
             L.ax = k.x; L.ay = k.y; L.cx = k.z; L.cy = k.w; L.w = g.x; L.h = g.y; L.pitch = g.z;
             L.img = reinterpret_cast<const uchar4*>(__ldg(reinterpret_cast<const unsigned long long*>(&V->lv[l].img)));
         }
-        // derivative step (patch_sampler.cc:94-100)
-        float ax_, ay_, bx_, by_;
-        project(V, L, cpx + crx, cpy + cry, cpz + crz, ax_, ay_);
-        project(V, L, cpx, cpy, cpz, bx_, by_);
-        const float ddx = ax_ - bx_, ddy = ay_ - by_;
+        // every lane projects its own patch point; the spare lane 25 projects patchPoints[12] + masterViewDirs[12]
+        // so that the derivative step (patch_sampler.cc:94-100) costs no extra instructions
+        const bool aux = lane == NS;
+        float qx, qy;
+        project(w, L, aux ? cpx + crx : px, aux ? cpy + cry : py, aux ? cpz + crz : pz, qx, qy);
+        const float ddx = __shfl_sync(FULL, qx, NS) - __shfl_sync(FULL, qx, CENTER);
+        const float ddy = __shfl_sync(FULL, qy, NS) - __shfl_sync(FULL, qy, CENTER);
         const float dd = sqrtf(ddx * ddx + ddy * ddy);
         const bool dok = dd > 0.f;
         const float step = 1.f / dd;
-        float qx, qy;
-        project(V, L, px, py, pz, qx, qy);
         const bool inb = qx > 0.f && qx < (float)(L.w - 1) && qy > 0.f && qy < (float)(L.h - 1);
         if (!__all_sync(FULL, inb || !act)) return 0u;
         if (act) {
             float gx = 0.f, gy = 0.f;
             if (dok) {
                 float tx, ty;
-                project(V, L, px + rx * step, py + ry * step, pz + rz * step, tx, ty);
+                project(w, L, px + rx * step, py + ry * step, pz + rz * step, tx, ty);
                 gx = tx - qx; gy = ty - qy;
             }
             const int left = (int)floorf(qx), top = (int)floorf(qy);
@@ -279,20 +291,32 @@ struct Patch {
         return tmp > 0.f ? devXY / tmp : -1.f;
     }
 
-    // One pass over the selected views at the current state (see the header comment).
+    // One pass at the current state (see the header comment).
+    //   candidates : false -> over the selected views; true -> over the AVAILABLE global views, only their NCC is
+    //                computed (first half of LocalViewSelection::performVS, local_view_selection.cc:73-85)
     //   cs_pending : a computeColorScale() is due at this state (patch_optimization.cc:77,198,230)
     //   want_ncc   : the NCCs of this state are read by the reference (getFastNCC, patch_optimization.cc:192,213,126)
     //   want_normal: the next Gauss-Newton step is optimizeDepthAndNormal (else optimizeDepthOnly)
-    __device__ __noinline__ void pass(bool cs_pending, bool want_ncc, bool want_normal)
+    // This is the only place a sample set is drawn, so its code exists once in the kernel.
+    __device__ __forceinline__ void pass(bool candidates, bool cs_pending, bool want_ncc, bool want_normal)
     {
-        p_col_ok = p_der_ok = 0u;
         float num = 0.f, den = 0.f;
         double A0 = 0, A1 = 0, A2 = 0, A3 = 0, A4 = 0, A5 = 0, B0 = 0, B1 = 0, B2 = 0;
         bool cs_active = cs_pending && st->use_color_scale;
-        for (int k = 0; k < nsel; ++k) {
-            const int slot = __shfl_sync(FULL, sel_l, k);
+        if (!candidates) { p_col_ok = p_der_ok = 0u; }
+        const int count = candidates ? job->n_global : nsel;
+        for (int k = 0; k < count; ++k) {
+            int slot = k;
+            if (candidates) { if (!((avail >> k) & 1u)) continue; }
+            else slot = __shfl_sync(FULL, sel_l, k);
             float n[3], d[3];
             const unsigned r = sample(&views[job->gview[slot]], n, d);
+            if (candidates) {
+                const float v = (r & 1u) ? ncc_of(n) : -1.f;
+                if (v < st->min_ncc) avail &= ~(1u << k);
+                else if (lane == k) cand_ncc_l = v;
+                continue;
+            }
             if (r & 1u) p_col_ok |= 1u << k;
             if (r & 2u) p_der_ok |= 1u << k;
             if (want_ncc) {
@@ -343,9 +367,11 @@ struct Patch {
                 }
             }
         }
+        if (candidates) return;
         p_num = warp_sum(num);
         p_den = warp_sum(den);
         p_has_normal = want_normal;
+        p_has_ncc = want_ncc;
         if (want_normal) {
             pA0 = warp_sum(A0); pA1 = warp_sum(A1); pA2 = warp_sum(A2); pA3 = warp_sum(A3); pA4 = warp_sum(A4); pA5 = warp_sum(A5);
             pB0 = warp_sum(B0); pB1 = warp_sum(B1); pB2 = warp_sum(B2);
@@ -436,29 +462,18 @@ struct Patch {
     static __device__ __forceinline__ float clamp1(float v) { return v < -1.f ? -1.f : (v > 1.f ? 1.f : v); }
     static __device__ __forceinline__ float deg_acos(float dp) { return acosf(dp) * 180.f / 3.141592653589793f; }
 
-    // LocalViewSelection::performVS (local_view_selection.cc:57-147); lane i evaluates candidate slot i.
-    __device__ __noinline__ void lvs_perform()
+    // Second half of LocalViewSelection::performVS (local_view_selection.cc:86-147): greedy selection among the
+    // candidates that survived the NCC test of pass(candidates = true); lane i evaluates candidate slot i.
+    __device__ __forceinline__ void lvs_greedy()
     {
         const unsigned N = st->nr_recon_neighbors;
-        if ((unsigned)nsel == N) { lvs_ok = true; return; }
         const float cs_init = 1.f / mm;
-        // refDir
         float rdx = cpx - __ldg(&rv->campos[0]), rdy = cpy - __ldg(&rv->campos[1]), rdz = cpz - __ldg(&rv->campos[2]);
         {
             const float nn = sqrtf(rdx * rdx + rdy * rdy + rdz * rdz);
             rdx /= nn; rdy /= nn; rdz /= nn;
         }
-        // NCC of every available global view (one sample set each); lane i keeps candidate i's value
-        float my_ncc = 0.f;
         const int G = job->n_global;
-        for (int i = 0; i < G; ++i) {
-            if (!((avail >> i) & 1u)) continue;
-            float tn[3], td[3];
-            const unsigned r = sample(&views[job->gview[i]], tn, td);
-            const float v = (r & 1u) ? ncc_of(tn) : -1.f;
-            if (v < st->min_ncc) { avail &= ~(1u << i); continue; }
-            if (lane == i) my_ncc = v;
-        }
         // per-lane candidate geometry (viewDir, epipolarPlane, footprint)
         float vdx = 0.f, vdy = 0.f, vdz = 1.f, epx = 0.f, epy = 0.f, epz = 1.f, nfp = 1.f;
         if (lane < G) {
@@ -478,7 +493,7 @@ struct Patch {
             const bool mine = lane < G && ((avail >> lane) & 1u);
             float score = -1.f;
             if (mine) {
-                score = my_ncc;
+                score = cand_ncc_l;
                 if (mfp / nfp < 0.5f) score *= 0.01f;
                 float dp = clamp1(rdx * vdx + rdy * vdy + rdz * vdz);
                 score *= plx_weight(deg_acos(dp));
@@ -511,15 +526,16 @@ struct Patch {
         if ((unsigned)nsel == N) lvs_ok = true;
     }
 
-    // PatchOptimization ctor (patch_optimization.cc:21-78) incl. LocalViewSelection ctor (local_view_selection.cc:19-54)
+    // PatchOptimization ctor (patch_optimization.cc:21-78) incl. LocalViewSelection ctor (local_view_selection.cc:19-54),
+    // up to the point where the first sample sets are needed.
     __device__ __forceinline__ void init(const PatchIn& in)
     {
         rv = &views[job->ref_view];
         depth = in.depth; dzI = in.dzI; dzJ = in.dzJ;
         iter = 0; opti = true; converged = false; lvs_ok = false;
         nsel = 0; avail = 0u;
-        sel_l = 0xFF; cs0_l = cs1_l = cs2_l = 0.f; ncc_l = 0.f;
-        p_col_ok = p_der_ok = 0u; p_num = p_den = 0.f; p_has_normal = false;
+        sel_l = 0xFF; cs0_l = cs1_l = cs2_l = 0.f; ncc_l = 0.f; cand_ncc_l = 0.f;
+        p_col_ok = p_der_ok = 0u; p_num = p_den = 0.f; p_has_normal = p_has_ncc = false;
         pA0 = pA1 = pA2 = pA3 = pA4 = pA5 = pB0 = pB1 = pB2 = 0.0;
         init_sampler(in.x, in.y);
         // propagated ids arrive ascending, 0xFF padded
@@ -530,67 +546,72 @@ struct Patch {
         if ((unsigned)nsel == N) lvs_ok = true;
         else if ((unsigned)nsel > N) { nsel = 0; sel_l = 0xFF; }
         avail = job->n_global >= 32 ? FULL : ((1u << job->n_global) - 1u);
-        {
-            unsigned m = 0u;
-            for (int k = 0; k < nsel; ++k) m |= 1u << __shfl_sync(FULL, sel_l, k);
-            avail &= ~m;
-        }
-        const float cs_init = 1.f / mm;
-        cs0_l = cs1_l = cs2_l = cs_init;
-        lvs_perform();
-        if (!lvs_ok) { opti = false; return; }
+        unsigned m = 0u;
+        for (int k = 0; k < nsel; ++k) m |= 1u << __shfl_sync(FULL, sel_l, k);
+        avail &= ~m;
+        cs0_l = cs1_l = cs2_l = 1.f / mm;
     }
 
-    // PatchOptimization::doAutoOptimization (patch_optimization.cc:170-242) on top of passes.
+    // The rest of the ctor (performVS, computeColorScale) and PatchOptimization::doAutoOptimization
+    // (patch_optimization.cc:66-77,170-242) as a state machine around the single pass() call site.
     __device__ __forceinline__ void auto_optimize()
     {
-        if (!lvs_ok || !opti) return;
-        // ctor's computeColorScale() at the initial state + the terms of the first depth step
-        pass(true, false, false);
         if (!opti) return;
-        // first four iterations only refine depth (:177-180)
-        while (iter < 4 && opti) {
-            const bool moved = depth_step();
-            ++iter;
-            if (moved && opti) pass(false, iter == 4, iter == 4);
-        }
-        bool viewRemoved = false;
-        while ((unsigned)iter < st->max_iterations && lvs_ok && opti) {
-            // oldNCC (:190-193): NCCs of the current state.  They are in ncc_l unless the state did not move since a
-            // pass without NCCs (only possible when a depth step had denom <= 0).
-            const bool normal = (iter % 5 == 4) || viewRemoved;
-            if ((normal && !p_has_normal) || iter == 4) {
-                // (re)draw the current state with everything this iteration reads
-                if (!(iter == 4 && p_has_normal)) pass(false, true, normal);
+        enum Stage { LVS_CTOR, CTOR, FIRST, PRE, POST, LVS_REPL, REPL };
+        int stage = lvs_ok ? CTOR : LVS_CTOR;
+        bool viewRemoved = false, was_normal = false, normal = false;
+        float old = 0.f;
+        for (;;) {
+            // arguments of the one pass() call, by stage
+            const bool a_cand = (stage == LVS_CTOR) | (stage == LVS_REPL);
+            const bool a_cs = (stage == CTOR) | (stage == REPL) | ((stage == POST) & was_normal);   // computeColorScale of :77, :230, :198
+            const bool a_ncc = (stage == PRE) | (stage == POST) | (stage == REPL) | ((stage == FIRST) & (iter == 4));
+            const bool a_normal = (stage == REPL) | ((stage == FIRST) & (iter == 4)) | ((stage == PRE) & normal) |
+                                  ((stage == POST) & ((iter + 1) % 5 == 4));
+            pass(a_cand, a_cs, a_ncc, a_normal);
+            if (stage == LVS_CTOR || stage == LVS_REPL) {
+                lvs_greedy();
+                if (!lvs_ok) { if (stage == LVS_CTOR) opti = false; return; }
+                stage = (stage == LVS_CTOR) ? CTOR : REPL;
+                continue;
             }
-            const float old = ncc_l;
+            if (!opti) return;            // a colour scale failed: every caller of computeColorScale gives up here
+            if (stage == POST) {
+                const float df = fabsf(ncc_l - old);
+                const bool mine = lane < nsel;
+                const bool conv = !__any_sync(FULL, mine && df > st->min_refine_diff);
+                const unsigned tbr = __ballot_sync(FULL, mine && (ncc_l < st->accept_ncc || (iter == 14 && df > st->min_refine_diff)));
+                if (tbr) {
+                    viewRemoved = true;
+                    sel_erase_mask(tbr);          // LocalViewSelection::replaceViews (local_view_selection.cc:150-160)
+                    lvs_ok = false;
+                    stage = LVS_REPL;
+                    continue;
+                }
+                if (conv) { converged = true; return; }
+                ++iter;
+            } else if (stage == REPL) {
+                ++iter;
+            }
+            // first four iterations only refine depth (:177-180)
+            bool need_pass = false;
+            while (iter < 4 && opti) {
+                const bool moved = depth_step();
+                ++iter;
+                if (moved && opti) { stage = FIRST; need_pass = true; break; }
+            }
+            if (need_pass) continue;
+            if (!opti) return;
+            // head of the main loop (:184-203)
+            if (!((unsigned)iter < st->max_iterations && lvs_ok)) return;
+            normal = (iter % 5 == 4) || viewRemoved;
+            if (!p_has_ncc || (normal && !p_has_normal)) { stage = PRE; continue; }   // only after a depth step with denom <= 0
+            old = ncc_l;                  // oldNCC (:190-193)
             opti = false;
-            bool moved;
-            if (normal) { moved = normal_step(); viewRemoved = false; }
-            else moved = depth_step();
+            if (normal) { normal_step(); viewRemoved = false; was_normal = true; }
+            else { depth_step(); was_normal = false; }
             if (!opti) return;
-            (void)moved;
-            // new state: NCCs, the colour-scale update that follows a depth+normal step (:198), next step's terms
-            const bool next_normal = ((iter + 1) % 5 == 4);
-            pass(normal, true, next_normal);
-            if (!opti) return;
-            const float df = fabsf(ncc_l - old);
-            const bool mine = lane < nsel;
-            const bool conv = !__any_sync(FULL, mine && df > st->min_refine_diff);
-            const unsigned tbr = __ballot_sync(FULL, mine && (ncc_l < st->accept_ncc || (iter == 14 && df > st->min_refine_diff)));
-            if (tbr) {
-                viewRemoved = true;
-                // LocalViewSelection::replaceViews (local_view_selection.cc:150-160)
-                sel_erase_mask(tbr);
-                lvs_ok = false;
-                lvs_perform();
-                if (!lvs_ok) return;
-                pass(true, true, true);                    // computeColorScale() of :230 on the new set (+ next terms)
-            } else if (conv) {
-                converged = true;
-                return;
-            }
-            ++iter;
+            stage = POST;
         }
     }
 

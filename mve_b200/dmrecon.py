@@ -83,8 +83,8 @@ def lib():
     global _LIB
     if _LIB is not None:
         return _LIB
-    path = _build.LIB
-    if _build.needs_build():
+    path = os.environ.get("B200MVS_LIB") or _build.LIB      # B200MVS_LIB: kernel-variant experiments (tools/kbench.py)
+    if path == _build.LIB and _build.needs_build():
         path = _build.build()
     L = C.CDLL(path)
     L.b200mvs_last_error.restype = C.c_char_p
