@@ -171,8 +171,15 @@ bool in_aabb(const float* p, const b200mvs_settings& s)
 }
 
 // DMRecon::analyzeFeatures (dmrecon.cc:179-208) + GlobalViewSelection (global_view_selection.cc:17-101).
-// Kept on the host: it is O(views x features) once per reference view and its INTEGER result must match the
-// reference bit for bit, so it uses the reference's float expression order.
+// Kept on the host: its INTEGER result must match the reference bit for bit, so every float is produced by the
+// reference's expression order.  What is restructured is only WHEN things are computed:
+//   * (feature - camera centre).normalized() is computed once per (view, feature) instead of inside every parallax()
+//     call (mvs_tools.h:46-53) - same operations, same values;
+//   * `if (plx < minParallax) score *= sqr(plx / 10)` (global_view_selection.cc:80-81,93-97) needs acos only when the
+//     directions are nearly parallel: for dot < cos(minParallax + 0.05 deg) the branch is certainly not taken;
+//   * the factor of a selected view s on (candidate i, feature k) does not change between rounds; multiplying by the
+//     exact 1.0f of a not-taken branch cannot change a rounding, so only the rare factors != 1 are stored (ascending s,
+//     the std::set iteration order) and re-multiplied each round.
 std::vector<int> global_view_selection(const b200mvs_ctx* c, const b200mvs_settings& st, int ref)
 {
     const int nv = (int)c->views.size();
@@ -188,13 +195,57 @@ std::vector<int> global_view_selection(const b200mvs_ctx* c, const b200mvs_setti
             if (point_in_frustum(c->views[vid], f.pos)) featInd[vid].push_back((int)i);
         }
     }
-    // SingleView::seesFeature (single_view.h:166-174) as a dense bit table
     const size_t nf = c->feats.size();
-    std::vector<std::vector<bool>> sees(nv);
+    const float dot_skip = (float)std::cos(((double)st.min_parallax + 0.05) * 3.14159265358979323846 / 180.0);
+    auto unit_dir = [&](const HostView& v, const float* p, float* d) {
+        d[0] = p[0] - v.campos[0]; d[1] = p[1] - v.campos[1]; d[2] = p[2] - v.campos[2];
+        normalize3(d);
+    };
+    // parallax factor of global_view_selection.cc:80-81 / :93-97 from two unit directions
+    auto plx_factor = [&](const float* d1, const float* d2) -> float {
+        const float dt = dot3(d1, d2);
+        if (dt < dot_skip) return 1.f;
+        const float dp = std::max(std::min(dt, 1.f), -1.f);
+        const float plx = std::acos(dp) * 180.f / 3.141592653589793f;
+        if (plx < st.min_parallax) { const float q = plx / 10.f; return q * q; }
+        return 1.f;
+    };
+    struct Cand {
+        std::vector<float> dir;          // 3 floats per entry of featInd[i]
+        std::vector<float> base;         // parallax-with-ref and resolution terms (:78-87)
+        std::vector<unsigned char> taken_ref;   // whether the ref-parallax branch multiplied (keeps `score = 1 * q*q` order)
+        std::vector<std::vector<std::pair<int, float>>> extra;   // factors != 1 of selected views, ascending view id
+    };
+    std::vector<Cand> cand(nv);
     std::vector<char> avail(nv, 1);
     avail[ref] = 0;
     for (int v = 0; v < nv; ++v) if (!c->views[v].valid) avail[v] = 0;
+    for (int i = 0; i < nv; ++i) {
+        if (!avail[i]) continue;
+        const HostView& tv = c->views[i];
+        Cand& C = cand[i];
+        const size_t n = featInd[i].size();
+        C.dir.resize(3 * n); C.base.resize(n); C.extra.resize(n);
+        for (size_t k = 0; k < n; ++k) {
+            const float* fp = c->feats[featInd[i][k]].pos;
+            float dr[3];
+            unit_dir(rv, fp, dr);
+            unit_dir(tv, fp, &C.dir[3 * k]);
+            float score = 1.f;
+            score *= plx_factor(dr, &C.dir[3 * k]);
+            const float mfp = foot_print(rv, st.scale, fp);
+            const float nfp = foot_print(tv, 0, fp);
+            float ratio = mfp / nfp;
+            if (ratio > 2.) ratio = (float)(2. / ratio);
+            else if (ratio > 1.) ratio = 1.;
+            score *= ratio;
+            C.base[k] = score;
+        }
+    }
+    // SingleView::seesFeature (single_view.h:166-174) as a dense table; direction of a selected view per feature id
     std::vector<int> selected;
+    std::vector<std::vector<float>> sel_dir(nv);     // [view][3 * feature id], filled when the view gets selected
+    std::vector<std::vector<bool>> sees(nv);
     bool found = true;
     while (found && selected.size() < st.global_vs_max) {
         float maxBenefit = 0.f;
@@ -202,32 +253,40 @@ std::vector<int> global_view_selection(const b200mvs_ctx* c, const b200mvs_setti
         found = false;
         for (int i = 0; i < nv; ++i) {
             if (!avail[i]) continue;
-            const HostView& tv = c->views[i];
+            const Cand& C = cand[i];
             float benefit = 0;
-            for (int fid : featInd[i]) {
-                float score = 1.f;
-                const float* fp = c->feats[fid].pos;
-                float plx = parallax(fp, rv, tv);
-                if (plx < st.min_parallax) { const float q = plx / 10.f; score *= q * q; }
-                const float mfp = foot_print(rv, st.scale, fp);
-                const float nfp = foot_print(tv, 0, fp);
-                float ratio = mfp / nfp;
-                if (ratio > 2.) ratio = (float)(2. / ratio);
-                else if (ratio > 1.) ratio = 1.;
-                score *= ratio;
-                for (int sv : selected) {
-                    if (sees[sv].empty()) { sees[sv].assign(nf, false); for (int q : featInd[sv]) sees[sv][q] = true; }
-                    if (!sees[sv][fid]) continue;
-                    plx = parallax(fp, c->views[sv], tv);
-                    if (plx < st.min_parallax) { const float q = plx / 10.f; score *= q * q; }
-                }
+            const size_t n = featInd[i].size();
+            for (size_t k = 0; k < n; ++k) {
+                float score = C.base[k];
+                for (const std::pair<int, float>& e : C.extra[k]) score *= e.second;
                 benefit += score;
             }
             if (benefit > maxBenefit) { maxBenefit = benefit; maxView = i; found = true; }
         }
-        if (found) {
-            selected.insert(std::upper_bound(selected.begin(), selected.end(), maxView), maxView);
-            avail[maxView] = 0;
+        if (!found) break;
+        selected.insert(std::upper_bound(selected.begin(), selected.end(), maxView), maxView);
+        avail[maxView] = 0;
+        // fold the new view's factors into every remaining candidate
+        const int sv = maxView;
+        sees[sv].assign(nf, false);
+        sel_dir[sv].assign(3 * nf, 0.f);
+        for (size_t k = 0; k < featInd[sv].size(); ++k) {
+            const int fid = featInd[sv][k];
+            sees[sv][fid] = true;
+            std::memcpy(&sel_dir[sv][3 * (size_t)fid], &cand[sv].dir[3 * k], 12);
+        }
+        for (int i = 0; i < nv; ++i) {
+            if (!avail[i]) continue;
+            Cand& C = cand[i];
+            for (size_t k = 0; k < featInd[i].size(); ++k) {
+                const int fid = featInd[i][k];
+                if (!sees[sv][fid]) continue;
+                const float f = plx_factor(&sel_dir[sv][3 * (size_t)fid], &C.dir[3 * k]);
+                if (f != 1.f) {
+                    std::vector<std::pair<int, float>>& ex = C.extra[k];
+                    ex.insert(std::upper_bound(ex.begin(), ex.end(), std::make_pair(sv, -1e30f)), std::make_pair(sv, f));
+                }
+            }
         }
     }
     return selected;
@@ -333,6 +392,9 @@ constexpr int OPT_WARPS = 4;
 #endif
 
 // One warp per queue entry: PatchOptimization ctor + doAutoOptimization + computeConfidence.
+// (An 8-lanes-per-patch mapping was tried: 28 % fewer instructions but 4x the loop body, i-cache misses and a 75 % L1
+// hit rate made it 14 % slower - profiles/r1_notes.md.)
+constexpr int OPT_ENTRIES_PER_BLOCK = OPT_WARPS;
 __global__ void __launch_bounds__(OPT_WARPS * 32, OPT_MIN_BLOCKS)
 k_optimize(const Entry* __restrict__ in, PatchOut* __restrict__ out, const unsigned long long* __restrict__ n_ptr, int n_max,
            const DevSettings* __restrict__ st, const JobParams* __restrict__ jobs, const ViewParams* __restrict__ views,
@@ -342,10 +404,10 @@ k_optimize(const Entry* __restrict__ in, PatchOut* __restrict__ out, const unsig
     for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = g_lut[i];
     __syncthreads();
     const int lane = threadIdx.x & 31;
-    const int wid = blockIdx.x * OPT_WARPS + (threadIdx.x >> 5);
+    const int eid = blockIdx.x * OPT_ENTRIES_PER_BLOCK + (threadIdx.x >> 5);
     const int n = n_ptr ? (int)min((unsigned long long)n_max, *n_ptr) : n_max;
-    if (wid >= n) return;
-    const Entry e = in[wid];
+    if (eid >= n) return;
+    const Entry e = in[eid];
     PatchIn pi;
     pi.x = e.xy & 0xFFFF; pi.y = (e.xy >> 16) & 0xFFFF;
     pi.depth = e.depth; pi.dzI = e.dzI; pi.dzJ = e.dzJ; pi.slots = e.slots;
@@ -353,7 +415,7 @@ k_optimize(const Entry* __restrict__ in, PatchOut* __restrict__ out, const unsig
     PatchOut po;
     const unsigned sets = optimize_patch(st, job, views, lut, lane, pi, po);
     if (lane == 0) {
-        out[wid] = po;
+        out[eid] = po;
         atomicAdd(&counters[C_SETS], (unsigned long long)sets);
         atomicAdd(&counters[C_OPTS], 1ull);
     }
@@ -851,7 +913,7 @@ int b200mvs_optimize_patches(b200mvs_ctx* ctx, const b200mvs_settings* s, int re
     CK(cudaMemsetAsync(ctx->counters.p, 0, sizeof(unsigned long long) * C_NUM, st));
     cudaEvent_t e0 = get_event(ctx, 0), e1 = get_event(ctx, 1);
     CK(cudaEventRecord(e0, st));
-    k_optimize<<<(n + OPT_WARPS - 1) / OPT_WARPS, OPT_WARPS * 32, 0, st>>>(ctx->run_in.p, ctx->run_out.p, nullptr, n, ctx->d_settings.p,
+    k_optimize<<<(n + OPT_ENTRIES_PER_BLOCK - 1) / OPT_ENTRIES_PER_BLOCK, OPT_WARPS * 32, 0, st>>>(ctx->run_in.p, ctx->run_out.p, nullptr, n, ctx->d_settings.p,
                                                                          ctx->d_jobs.p, ctx->d_views, ctx->d_lut, ctx->counters.p);
     CK(cudaGetLastError());
     CK(cudaEventRecord(e1, st));
@@ -1014,7 +1076,7 @@ int b200mvs_reconstruct(b200mvs_ctx* ctx, const b200mvs_settings* s, int n_refs,
         cudaEvent_t a = get_event(ctx, n_ev), b = get_event(ctx, n_ev + 1);
         opt_events.push_back({n_ev, n_ev + 1}); n_ev += 2;
         CK(cudaEventRecord(a, st));
-        k_optimize<<<(ns + OPT_WARPS - 1) / OPT_WARPS, OPT_WARPS * 32, 0, st>>>(ctx->run_in.p, ctx->run_out.p, nullptr, ns, ctx->d_settings.p,
+        k_optimize<<<(ns + OPT_ENTRIES_PER_BLOCK - 1) / OPT_ENTRIES_PER_BLOCK, OPT_WARPS * 32, 0, st>>>(ctx->run_in.p, ctx->run_out.p, nullptr, ns, ctx->d_settings.p,
                                                                               ctx->d_jobs.p, ctx->d_views, ctx->d_lut, d_cnt);
         CK(cudaEventRecord(b, st));
         k_seed_select<<<(ns + 255) / 256, 256, 0, st>>>(ctx->run_in.p, ctx->run_out.p, ns, ctx->d_jobs.p, d_cnt);
@@ -1049,7 +1111,7 @@ int b200mvs_reconstruct(b200mvs_ctx* ctx, const b200mvs_settings* s, int n_refs,
         cudaEvent_t a = get_event(ctx, n_ev), b = get_event(ctx, n_ev + 1);
         opt_events.push_back({n_ev, n_ev + 1}); n_ev += 2;
         CK(cudaEventRecord(a, st));
-        k_optimize<<<(n + OPT_WARPS - 1) / OPT_WARPS, OPT_WARPS * 32, 0, st>>>(ctx->run_in.p, ctx->run_out.p, d_cnt + C_RUN, n, ctx->d_settings.p,
+        k_optimize<<<(n + OPT_ENTRIES_PER_BLOCK - 1) / OPT_ENTRIES_PER_BLOCK, OPT_WARPS * 32, 0, st>>>(ctx->run_in.p, ctx->run_out.p, d_cnt + C_RUN, n, ctx->d_settings.p,
                                                                              ctx->d_jobs.p, ctx->d_views, ctx->d_lut, d_cnt);
         CK(cudaEventRecord(b, st));
         k_commit<<<(n + 255) / 256, 256, 0, st>>>(ctx->run_in.p, ctx->run_out.p, d_cnt + C_RUN, ctx->d_jobs.p, ctx->written.p, d_cnt, d_filled);

@@ -95,6 +95,14 @@ __device__ __forceinline__ float warp_max(float v)
     return v;
 }
 
+// Hot-path approximations (each <= 2 ulp): MUFU reciprocal / reciprocal square root instead of the IEEE division and
+// square root sequences (which cost ~10 instructions + a slow-path branch each and made up ~16 % of the kernel).  The
+// reference itself is built with -funsafe-math-optimizations (Makefile.inc:5), i.e. without IEEE guarantees for these
+// operations; the effect on parity is measured by tests/test_gpu_parity.py.  Everything that decides integers on the
+// host (global view selection, seeds, pyramid) stays IEEE.
+__device__ __forceinline__ float rcp_fast(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float rsqrt_fast(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
 struct Patch {
     // ---- constants of the patch ----
     const DevSettings* st;
@@ -113,7 +121,7 @@ struct Patch {
     // ---- warp-uniform state ----
     float crx, cry, crz;       // masterViewDirs[12]
     float cpx, cpy, cpz;       // patchPoints[12]
-    float mfp;                 // footPrintScaled(patchPoints[12])
+    float mfp, inv_mfp;        // footPrintScaled(patchPoints[12]) and its reciprocal
     float mm, sqrDevX;         // masterMeanCol, sqrDevX
     float depth, dzI, dzJ;
     bool ref_ok;               // sampler->success[refViewNr]
@@ -129,7 +137,8 @@ struct Patch {
     // ---- results of the last pass (valid for the current state and selected set) ----
     unsigned p_col_ok, p_der_ok;   // bit k: colour / derivative path of selected view k succeeded
     float p_num, p_den;            // optimizeDepthOnly sums
-    double pA0, pA1, pA2, pA3, pA4, pA5, pB0, pB1, pB2;   // optimizeDepthAndNormal sums
+    float nX0, nX1, nX2;           // solution of the 3x3 normal equations of optimizeDepthAndNormal
+    bool n_singular;               // detATA == 0 (patch_optimization.cc:347-351)
     bool p_has_normal, p_has_ncc;
     float cand_ncc_l;          // NCC of candidate global slot `lane` (local view selection)
 
@@ -142,7 +151,7 @@ struct Patch {
         const float c0 = w[0] * X + w[1] * Y + w[2] * Z + w[3];
         const float c1 = w[4] * X + w[5] * Y + w[6] * Z + w[7];
         const float c2 = w[8] * X + w[9] * Y + w[10] * Z + w[11];
-        const float ic2 = __frcp_rn(c2);
+        const float ic2 = rcp_fast(c2);
         x = (L.ax * c0 + L.cx * c2) * ic2 - 0.5f;
         y = (L.ay * c1 + L.cy * c2) * ic2 - 0.5f;
     }
@@ -161,6 +170,7 @@ struct Patch {
         cpz = __shfl_sync(FULL, pz, CENTER);
         const float z = __ldg(&rv->w2c[8]) * cpx + __ldg(&rv->w2c[9]) * cpy + __ldg(&rv->w2c[10]) * cpz + __ldg(&rv->w2c[11]);
         mfp = z * job->ki0;     // single_view.h:160-164
+        inv_mfp = rcp_fast(mfp);
     }
 
     // PatchSampler ctor (patch_sampler.cc:19-62) + computeMasterSamples (:298-345)
@@ -171,7 +181,7 @@ struct Patch {
         fi = (float)di; fj = (float)dj;
         ref_ok = false; mm = 0.f; sqrDevX = 0.f; n_sets = 0u;
         rx = ry = rz = px = py = pz = 0.f; m0 = m1 = m2 = e0 = e1 = e2 = 0.f;
-        crx = cry = crz = cpx = cpy = cpz = mfp = 0.f;
+        crx = cry = crz = cpx = cpy = cpz = mfp = inv_mfp = 0.f;
         if (x - 2 < 0 || y - 2 < 0 || x + 2 > job->W - 1 || y + 2 > job->H - 1) return;
         // viewRayScaled (single_view.cc:99-106, depthmap.cc:149-156)
         {
@@ -228,7 +238,7 @@ struct Patch {
         // mfp <= 0 makes the reference throw std::out_of_range (patch_sampler.cc:78-82); it cannot happen for
         // depth > 0 because the centre ray has positive camera z.  Treated as a failed view here.
         if (!(mfp > 0.f) || nfp <= 0.f) return 0u;
-        float ratio = nfp / mfp;
+        float ratio = nfp * inv_mfp;
         int l = 0;
         while (ratio < 0.5f) { ++l; ratio *= 2.f; }
         const int nl = __ldg(&V->nlevels);
@@ -247,9 +257,10 @@ struct Patch {
         project(w, L, aux ? cpx + crx : px, aux ? cpy + cry : py, aux ? cpz + crz : pz, qx, qy);
         const float ddx = __shfl_sync(FULL, qx, NS) - __shfl_sync(FULL, qx, CENTER);
         const float ddy = __shfl_sync(FULL, qy, NS) - __shfl_sync(FULL, qy, CENTER);
-        const float dd = sqrtf(ddx * ddx + ddy * ddy);
+        const float dd2 = ddx * ddx + ddy * ddy;
+        const float dd = dd2 * rsqrt_fast(dd2);        // |.|; NaN for dd2 == 0, which fails `d > 0` like the reference's 0
         const bool dok = dd > 0.f;
-        const float step = 1.f / dd;
+        const float step = rcp_fast(dd);
         const bool inb = qx > 0.f && qx < (float)(L.w - 1) && qy > 0.f && qy < (float)(L.h - 1);
         if (!__all_sync(FULL, inb || !act)) return 0u;
         if (act) {
@@ -274,7 +285,7 @@ struct Patch {
                 const float x3 = (1.f - fx) * c[ch] + fx * e[ch];
                 n[ch] = (1.f - fy) * x0 + fy * x3;
                 const float der = gx * (b[ch] - a[ch]) + gy * (c[ch] - a[ch]) + (gy * fx + gx * fy) * (a[ch] - b[ch] - c[ch] + e[ch]);
-                d[ch] = dok ? der / step : 0.f;
+                d[ch] = dok ? der * dd : 0.f;        // deriv /= stepSize with stepSize = 1 / d (patch_sampler.cc:100,129-130)
             }
         }
         return dok ? 3u : 1u;
@@ -283,12 +294,13 @@ struct Patch {
     // getFastNCC on given colour samples (patch_sampler.cc:143-162)
     __device__ __forceinline__ float ncc_of(const float (&n)[3]) const
     {
-        const float my0 = warp_sum(n[0]) / (float)NS, my1 = warp_sum(n[1]) / (float)NS, my2 = warp_sum(n[2]) / (float)NS;
+        const float inv_n = 1.f / (float)NS;
+        const float my0 = warp_sum(n[0]) * inv_n, my1 = warp_sum(n[1]) * inv_n, my2 = warp_sum(n[2]) * inv_n;
         const float y0 = act ? n[0] - my0 : 0.f, y1 = act ? n[1] - my1 : 0.f, y2 = act ? n[2] - my2 : 0.f;
         const float sqrDevY = warp_sum(y0 * y0 + y1 * y1 + y2 * y2);
         const float devXY = warp_sum(e0 * y0 + e1 * y1 + e2 * y2);
-        const float tmp = sqrtf(sqrDevX * sqrDevY);
-        return tmp > 0.f ? devXY / tmp : -1.f;
+        const float p = sqrDevX * sqrDevY;              // devXY / sqrt(p), -1 when sqrt(p) is not > 0
+        return p > 0.f ? devXY * rsqrt_fast(p) : -1.f;
     }
 
     // One pass at the current state (see the header comment).
@@ -336,7 +348,7 @@ struct Patch {
                         const float ab = warp_sum((mc - n[ch] * cc[ch]) * n[ch]);
                         const float aa = warp_sum(n[ch] * n[ch]);
                         if ((double)fabsf(aa) > 1e-6) {
-                            cc[ch] += ab / aa;
+                            cc[ch] += ab * rcp_fast(aa);
                             if ((double)cc[ch] > 1e3) opti = false;
                         } else
                             opti = false;
@@ -373,8 +385,28 @@ struct Patch {
         p_has_normal = want_normal;
         p_has_ncc = want_ncc;
         if (want_normal) {
-            pA0 = warp_sum(A0); pA1 = warp_sum(A1); pA2 = warp_sum(A2); pA3 = warp_sum(A3); pA4 = warp_sum(A4); pA5 = warp_sum(A5);
-            pB0 = warp_sum(B0); pB1 = warp_sum(B1); pB2 = warp_sum(B2);
+            // solve here so that the nine fp64 sums die with the pass (matrix_tools.h:392-398,460-475)
+            A0 = warp_sum(A0); A1 = warp_sum(A1); A2 = warp_sum(A2); A3 = warp_sum(A3); A4 = warp_sum(A4); A5 = warp_sum(A5);
+            B0 = warp_sum(B0); B1 = warp_sum(B1); B2 = warp_sum(B2);
+            const double m[9] = {A0, A1, A2, A1, A3, A4, A2, A4, A5};
+            const double det = m[0] * m[4] * m[8] + m[1] * m[5] * m[6] + m[2] * m[3] * m[7]
+                             - m[2] * m[4] * m[6] - m[1] * m[3] * m[8] - m[0] * m[5] * m[7];
+            n_singular = det == 0.0;
+            double inv[9];
+            inv[0] = m[4] * m[8] - m[5] * m[7];
+            inv[1] = m[2] * m[7] - m[1] * m[8];
+            inv[2] = m[1] * m[5] - m[2] * m[4];
+            inv[3] = m[5] * m[6] - m[3] * m[8];
+            inv[4] = m[0] * m[8] - m[2] * m[6];
+            inv[5] = m[2] * m[3] - m[0] * m[5];
+            inv[6] = m[3] * m[7] - m[4] * m[6];
+            inv[7] = m[1] * m[6] - m[0] * m[7];
+            inv[8] = m[0] * m[4] - m[1] * m[3];
+#pragma unroll
+            for (int q = 0; q < 9; ++q) inv[q] /= det;
+            nX0 = (float)(inv[0] * B0 + inv[1] * B1 + inv[2] * B2);
+            nX1 = (float)(inv[3] * B0 + inv[4] * B1 + inv[5] * B2);
+            nX2 = (float)(inv[6] * B0 + inv[7] * B1 + inv[8] * B2);
         }
     }
 
@@ -393,30 +425,12 @@ struct Patch {
         return false;
     }
 
-    // optimizeDepthAndNormal (patch_optimization.cc:302-364, matrix_tools.h:392-398,460-475) from the last pass.
+    // optimizeDepthAndNormal (patch_optimization.cc:302-364) from the solution prepared by the last pass.
     __device__ __forceinline__ bool normal_step()
     {
         if (!all_der_ok()) { opti = false; return false; }
-        const double m[9] = {pA0, pA1, pA2, pA1, pA3, pA4, pA2, pA4, pA5};
-        const double det = m[0] * m[4] * m[8] + m[1] * m[5] * m[6] + m[2] * m[3] * m[7]
-                         - m[2] * m[4] * m[6] - m[1] * m[3] * m[8] - m[0] * m[5] * m[7];
-        if (det == 0.0) { opti = false; return false; }
-        double inv[9];
-        inv[0] = m[4] * m[8] - m[5] * m[7];
-        inv[1] = m[2] * m[7] - m[1] * m[8];
-        inv[2] = m[1] * m[5] - m[2] * m[4];
-        inv[3] = m[5] * m[6] - m[3] * m[8];
-        inv[4] = m[0] * m[8] - m[2] * m[6];
-        inv[5] = m[2] * m[3] - m[0] * m[5];
-        inv[6] = m[3] * m[7] - m[4] * m[6];
-        inv[7] = m[1] * m[6] - m[0] * m[7];
-        inv[8] = m[0] * m[4] - m[1] * m[3];
-#pragma unroll
-        for (int q = 0; q < 9; ++q) inv[q] /= det;
-        const float X0 = (float)(inv[0] * pB0 + inv[1] * pB1 + inv[2] * pB2);
-        const float X1 = (float)(inv[3] * pB0 + inv[4] * pB1 + inv[5] * pB2);
-        const float X2 = (float)(inv[6] * pB0 + inv[7] * pB1 + inv[8] * pB2);
-        dzI += X1; dzJ += X2; depth += X0;
+        if (n_singular) { opti = false; return false; }
+        dzI += nX1; dzJ += nX2; depth += nX0;
         update();
         opti = ref_ok;
         return true;
@@ -536,7 +550,7 @@ struct Patch {
         nsel = 0; avail = 0u;
         sel_l = 0xFF; cs0_l = cs1_l = cs2_l = 0.f; ncc_l = 0.f; cand_ncc_l = 0.f;
         p_col_ok = p_der_ok = 0u; p_num = p_den = 0.f; p_has_normal = p_has_ncc = false;
-        pA0 = pA1 = pA2 = pA3 = pA4 = pA5 = pB0 = pB1 = pB2 = 0.0;
+        nX0 = nX1 = nX2 = 0.f; n_singular = true;
         init_sampler(in.x, in.y);
         // propagated ids arrive ascending, 0xFF padded
         if (lane < MAX_LOCAL) sel_l = (in.slots >> (8 * lane)) & 0xFF;

@@ -54,6 +54,24 @@ def gvs_lines(scene_dir, scale, nrn, n_views, extra=()):
     return out
 
 
+def mint_gvs_only(name):
+    """Only the printed global view selections (many-candidate scene)."""
+    s = synth.make_scene(name)
+    synth.save_scene_npz(s, os.path.join(GOLD, "%s_scene.npz" % name))
+    s = synth.load_scene_npz(os.path.join(GOLD, "%s_scene.npz" % name))
+    tmp = tempfile.mkdtemp(prefix="golden_")
+    try:
+        synth.write_mve_scene(s, tmp)
+        data = {}
+        for tag, extra in (("gvs_default", ()), ("gvs_n3", ("-n3",))):
+            for v, ids in gvs_lines(tmp, s.scale, s.nr_recon_neighbors, s.n_views, extra).items():
+                data["%s_%d" % (tag, v)] = ids
+        np.savez_compressed(os.path.join(GOLD, "%s_ref.npz" % name), **data)
+        print(name, "gvs only;", "view 0 ->", data["gvs_default_0"])
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 def mint(name, map_views, n_patches=1500):
     s = synth.make_scene(name)
     synth.save_scene_npz(s, os.path.join(GOLD, "%s_scene.npz" % name))
@@ -115,3 +133,4 @@ if __name__ == "__main__":
     mint("T0", [0, 3])
     mint("T1", [4])
     mint("T2", [0])
+    mint_gvs_only("T3")

@@ -51,7 +51,7 @@ def test_pyramid_bit_exact(ctx, name):
         assert (g.level(4, 1) == golden_ref("T1")["undist_4"]).all()     # bytes written by the reference
 
 
-@pytest.mark.parametrize("name", ["T0", "T1", "T2"])
+@pytest.mark.parametrize("name", ["T0", "T1", "T2", "T3"])
 def test_global_view_selection_exact(ctx, name):
     s, g, o = ctx(name)
     ref = golden_ref(name)

@@ -47,7 +47,7 @@ def test_pyramid_bit_exact(osc):
     assert (sc.level(4, s.scale) == ref["undist_4"]).all()
 
 
-@pytest.mark.parametrize("name", ["T0", "T1", "T2"])
+@pytest.mark.parametrize("name", ["T0", "T1", "T2", "T3"])
 def test_global_view_selection_exact(osc, name):
     """Integer result of GlobalViewSelection (global_view_selection.cc:34-101) for default and -n 3."""
     s, sc = osc(name)
