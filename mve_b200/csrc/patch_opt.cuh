@@ -103,6 +103,37 @@ __device__ __forceinline__ float warp_max(float v)
 __device__ __forceinline__ float rcp_fast(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float rsqrt_fast(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
+// Batched butterflies: reducing K values together halves the number of live values at each of the first log2(K)
+// steps, so 4 sums cost 10 shuffles instead of 20 (2 sums: 7 instead of 10).  Every lane receives all totals, and all
+// lanes receive bitwise identical totals (each total is formed in exactly one lane group and then broadcast).
+__device__ __forceinline__ void warp_sum4(int lane, float& a, float& b, float& c, float& d)
+{
+    const bool h16 = lane & 16, h8 = lane & 8;
+    float k0 = h16 ? c : a, k1 = h16 ? d : b;
+    const float s0 = h16 ? a : c, s1 = h16 ? b : d;
+    k0 += __shfl_xor_sync(FULL, s0, 16);
+    k1 += __shfl_xor_sync(FULL, s1, 16);
+    float k = h8 ? k1 : k0;
+    const float s = h8 ? k0 : k1;
+    k += __shfl_xor_sync(FULL, s, 8);
+    k += __shfl_xor_sync(FULL, k, 4);
+    k += __shfl_xor_sync(FULL, k, 2);
+    k += __shfl_xor_sync(FULL, k, 1);
+    a = __shfl_sync(FULL, k, 0); b = __shfl_sync(FULL, k, 8); c = __shfl_sync(FULL, k, 16); d = __shfl_sync(FULL, k, 24);
+}
+__device__ __forceinline__ void warp_sum2(int lane, float& a, float& b)
+{
+    const bool h16 = lane & 16;
+    float k = h16 ? b : a;
+    const float s = h16 ? a : b;
+    k += __shfl_xor_sync(FULL, s, 16);
+    k += __shfl_xor_sync(FULL, k, 8);
+    k += __shfl_xor_sync(FULL, k, 4);
+    k += __shfl_xor_sync(FULL, k, 2);
+    k += __shfl_xor_sync(FULL, k, 1);
+    a = __shfl_sync(FULL, k, 0); b = __shfl_sync(FULL, k, 16);
+}
+
 struct Patch {
     // ---- constants of the patch ----
     const DevSettings* st;
@@ -295,10 +326,13 @@ struct Patch {
     __device__ __forceinline__ float ncc_of(const float (&n)[3]) const
     {
         const float inv_n = 1.f / (float)NS;
-        const float my0 = warp_sum(n[0]) * inv_n, my1 = warp_sum(n[1]) * inv_n, my2 = warp_sum(n[2]) * inv_n;
+        float my0 = n[0], my1 = n[1], my2 = n[2], pad = 0.f;
+        warp_sum4(lane, my0, my1, my2, pad);
+        my0 *= inv_n; my1 *= inv_n; my2 *= inv_n;
         const float y0 = act ? n[0] - my0 : 0.f, y1 = act ? n[1] - my1 : 0.f, y2 = act ? n[2] - my2 : 0.f;
-        const float sqrDevY = warp_sum(y0 * y0 + y1 * y1 + y2 * y2);
-        const float devXY = warp_sum(e0 * y0 + e1 * y1 + e2 * y2);
+        float sqrDevY = y0 * y0 + y1 * y1 + y2 * y2;
+        float devXY = e0 * y0 + e1 * y1 + e2 * y2;
+        warp_sum2(lane, sqrDevY, devXY);
         const float p = sqrDevX * sqrDevY;              // devXY / sqrt(p), -1 when sqrt(p) is not > 0
         return p > 0.f ? devXY * rsqrt_fast(p) : -1.f;
     }
@@ -313,7 +347,7 @@ struct Patch {
     __device__ __forceinline__ void pass(bool candidates, bool cs_pending, bool want_ncc, bool want_normal)
     {
         float num = 0.f, den = 0.f;
-        double A0 = 0, A1 = 0, A2 = 0, A3 = 0, A4 = 0, A5 = 0, B0 = 0, B1 = 0, B2 = 0;
+        float A0 = 0.f, A1 = 0.f, A2 = 0.f, A3 = 0.f, A4 = 0.f, A5 = 0.f, B0 = 0.f, B1 = 0.f, B2 = 0.f;
         bool cs_active = cs_pending && st->use_color_scale;
         if (!candidates) { p_col_ok = p_der_ok = 0u; }
         const int count = candidates ? job->n_global : nsel;
@@ -342,13 +376,14 @@ struct Patch {
                 if (!(r & 1u)) cs_active = false;
                 else {
                     float cc[3] = {c0, c1, c2};
+                    float ab[3] = {(m0 - n[0] * c0) * n[0], (m1 - n[1] * c1) * n[1], (m2 - n[2] * c2) * n[2]};
+                    float aa[3] = {n[0] * n[0], n[1] * n[1], n[2] * n[2]};
+                    warp_sum4(lane, ab[0], ab[1], ab[2], aa[0]);
+                    warp_sum2(lane, aa[1], aa[2]);
 #pragma unroll
                     for (int ch = 0; ch < 3; ++ch) {
-                        const float mc = ch == 0 ? m0 : (ch == 1 ? m1 : m2);
-                        const float ab = warp_sum((mc - n[ch] * cc[ch]) * n[ch]);
-                        const float aa = warp_sum(n[ch] * n[ch]);
-                        if ((double)fabsf(aa) > 1e-6) {
-                            cc[ch] += ab * rcp_fast(aa);
+                        if ((double)fabsf(aa[ch]) > 1e-6) {
+                            cc[ch] += ab[ch] * rcp_fast(aa[ch]);
                             if ((double)cc[ch] > 1e3) opti = false;
                         } else
                             opti = false;
@@ -372,23 +407,27 @@ struct Patch {
                         const float a0 = gg[ch];
                         const float a1 = fi * a0;      // (ii * cs) * deriv == ii * (cs * deriv) exactly for ii in {-2..2}
                         const float a2 = fj * a0;
-                        A0 += (double)(a0 * a0); A1 += (double)(a0 * a1); A2 += (double)(a0 * a2);
-                        A3 += (double)(a1 * a1); A4 += (double)(a1 * a2); A5 += (double)(a2 * a2);
-                        B0 += (double)(a0 * rr[ch]); B1 += (double)(a1 * rr[ch]); B2 += (double)(a2 * rr[ch]);
+                        A0 += a0 * a0; A1 += a0 * a1; A2 += a0 * a2;
+                        A3 += a1 * a1; A4 += a1 * a2; A5 += a2 * a2;
+                        B0 += a0 * rr[ch]; B1 += a1 * rr[ch]; B2 += a2 * rr[ch];
                     }
                 }
             }
         }
         if (candidates) return;
-        p_num = warp_sum(num);
-        p_den = warp_sum(den);
+        warp_sum2(lane, num, den);
+        p_num = num; p_den = den;
         p_has_normal = want_normal;
         p_has_ncc = want_ncc;
         if (want_normal) {
             // solve here so that the nine fp64 sums die with the pass (matrix_tools.h:392-398,460-475)
-            A0 = warp_sum(A0); A1 = warp_sum(A1); A2 = warp_sum(A2); A3 = warp_sum(A3); A4 = warp_sum(A4); A5 = warp_sum(A5);
-            B0 = warp_sum(B0); B1 = warp_sum(B1); B2 = warp_sum(B2);
-            const double m[9] = {A0, A1, A2, A1, A3, A4, A2, A4, A5};
+            // the lane's <= 12 products (3 channels x <= 4 views) are summed in fp32, the 25 lanes in fp64; the reference sums
+            // all 300 fp32 products in fp64 (patch_optimization.cc:336-342).  The difference (~1e-7 relative on ATA) is far
+            // below what the Gauss-Newton fixed point resolves; measured in tests/test_gpu_parity.py.
+            const double D0 = warp_sum((double)A0), D1 = warp_sum((double)A1), D2 = warp_sum((double)A2), D3 = warp_sum((double)A3);
+            const double D4 = warp_sum((double)A4), D5 = warp_sum((double)A5);
+            const double E0 = warp_sum((double)B0), E1 = warp_sum((double)B1), E2 = warp_sum((double)B2);
+            const double m[9] = {D0, D1, D2, D1, D3, D4, D2, D4, D5};
             const double det = m[0] * m[4] * m[8] + m[1] * m[5] * m[6] + m[2] * m[3] * m[7]
                              - m[2] * m[4] * m[6] - m[1] * m[3] * m[8] - m[0] * m[5] * m[7];
             n_singular = det == 0.0;
@@ -404,9 +443,9 @@ struct Patch {
             inv[8] = m[0] * m[4] - m[1] * m[3];
 #pragma unroll
             for (int q = 0; q < 9; ++q) inv[q] /= det;
-            nX0 = (float)(inv[0] * B0 + inv[1] * B1 + inv[2] * B2);
-            nX1 = (float)(inv[3] * B0 + inv[4] * B1 + inv[5] * B2);
-            nX2 = (float)(inv[6] * B0 + inv[7] * B1 + inv[8] * B2);
+            nX0 = (float)(inv[0] * E0 + inv[1] * E1 + inv[2] * E2);
+            nX1 = (float)(inv[3] * E0 + inv[4] * E1 + inv[5] * E2);
+            nX2 = (float)(inv[6] * E0 + inv[7] * E1 + inv[8] * E2);
         }
     }
 
