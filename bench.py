@@ -147,11 +147,11 @@ def run_reference_sample(scene_dir, scene, seconds, views):
         "oracle/mvs_oracle.cc port, %d views on %d threads, stopped after %.1f s" % (len(views), len(views), seconds)
 
 
-def reference_arm(args):
+def reference_arm(args, real_stdout):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    cfg = workload_cfg(args.workload, 1)
+    cfg = workload_cfg(args.workload, max(1, args.gpus))     # the same scene our arm reconstructs at this N
     cores = host_cores()
     budget = min(20.0, max(3.0, 150.0 / max(1, args.steps + args.warmup)))
     with tempfile.TemporaryDirectory(prefix="b200mvs_ref_") as tmp:
@@ -175,14 +175,31 @@ def reference_arm(args):
                              "host_cores_available": cores},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=real_stdout, flush=True)
     return 0
 
 
 # ----------------------------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------------------------
+def _protect_stdout():
+    """Everything but the one JSON line goes to stderr: libraries (NCCL prints its version banner on stdout) must not
+    pollute the line the driver parses.  Returns a file object bound to the original stdout."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 def main():
+    real_stdout = _protect_stdout()
+    try:
+        return _main(real_stdout)
+    finally:
+        real_stdout.flush()
+
+
+def _main(real_stdout):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -193,7 +210,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     args = ap.parse_args()
     if args.impl == "reference":
-        return reference_arm(args)
+        return reference_arm(args, real_stdout)
 
     import torch
     import torch.distributed as dist
@@ -365,7 +382,7 @@ def main():
                 "e2e": {"value": f_e2e_total / e2e_max, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "steps": e2e_steps, "ms_per_step": 1e3 * e2e_max / e2e_steps},
                 "roofline": roofline, "cpu_baseline": cpu_baseline}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=real_stdout, flush=True)
     if world > 1:
         dist.destroy_process_group()
     return 0

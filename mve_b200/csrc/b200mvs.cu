@@ -388,7 +388,7 @@ __global__ void k_export_rgb(const uchar4* __restrict__ src, int w, int h, int p
 // ------------------------------------------------------------------------------------------------
 constexpr int OPT_WARPS = 4;
 #ifndef OPT_MIN_BLOCKS
-#define OPT_MIN_BLOCKS 4     // registers per thread <= 65536 / (OPT_MIN_BLOCKS * 128); tuned on B200, profiles/r1_notes.md
+#define OPT_MIN_BLOCKS 5     // registers per thread <= 65536 / (OPT_MIN_BLOCKS * 128) -> 96; tuned on B200, profiles/r1_notes.md
 #endif
 
 // One warp per queue entry: PatchOptimization ctor + doAutoOptimization + computeConfidence.
