@@ -340,14 +340,23 @@ def _main(real_stdout):
     ms_kernel = sum(s.ms_patch_kernel for s in stats)
     n_launch = sum(int(s.n_patch_launches) for s in stats)
     achieved = (bpp * filled_local / (ms_kernel * 1e-3)) / 1e9 if ms_kernel > 0 and bpp > 0 else None
+    traffic, traffic_src = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_kopt_final_traffic.json")))
+        traffic = tj["dram_bytes_per_launch_mean"]
+        traffic_src = "ncu --set full capture of %d mid-run launches (%.0f patches each): profiles/r1_kopt_final_traffic.json" % (
+            len(tj["launches"]), tj["patches_per_launch_mean"])
+    except Exception:
+        pass
     roofline = {"kernel": "k_optimize (patch optimisation, one warp per queue entry)", "bound": "hbm",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                "traffic": None, "peak_source": peak_src,
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_filled_px": bpp,
                 "definition": "300 B x N_PSE + 75 B x N_opt + 28 B x N_filled with the oracle's strict-order counts per filled "
                               "pixel (profiles/scene_constants_%s.json) x filled pixels of the launch, / CUDA-event time of the "
                               "k_optimize launches in the timed region" % args.workload,
                 "avg_launch_ms": ms_kernel / max(1, n_launch), "launches": n_launch,
+                "algorithmic_bytes_per_launch_mean": (bpp * filled_local / max(1, n_launch)) if bpp > 0 else None,
                 "kernel_share_of_device_time": ms_kernel / max(1e-9, sum(s.ms_total_device for s in stats)),
                 "impl_sample_sets": sum(int(s.n_sample_sets) for s in stats), "impl_opts": sum(int(s.n_opt) for s in stats),
                 "impl_bytes_300_per_set_GBs": (300.0 * sum(int(s.n_sample_sets) for s in stats) / (ms_kernel * 1e-3) / 1e9) if ms_kernel > 0 else None}

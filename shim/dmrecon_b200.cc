@@ -12,6 +12,8 @@
 //                              image_pyramid.cc:99-132), b200mvs_reconstruct, results attached with View::set_image
 //                              under the reference's embedding names (depth-L<s>, dz-L<s>, conf-L<s>, undist-L<s>),
 //                              same log lines, Progress kept up to date, cancellation -> RECON_CANCELLED
+#include <atomic>
+#include <condition_variable>
 #include <cstring>
 #include <ctime>
 #include <iostream>
@@ -31,30 +33,108 @@
 
 namespace {
 
-// One device context per (scene, embedding), shared by all DMRecon objects of the process - the reference shares its
-// image pyramids the same way through ImagePyramidCache's statics (image_pyramid.cc:157-160).
-struct SharedCtx {
-    std::mutex mtx;
+// One device context per (scene, embedding) AND per GPU, shared by all DMRecon objects of the process - the reference
+// shares its image pyramids the same way through ImagePyramidCache's statics (image_pyramid.cc:157-160).
+//
+// The reference driver runs DMRecon::start() concurrently from OpenMP threads (apps/dmrecon/dmrecon.cc:285).  Here the
+// concurrent calls are (i) spread round-robin over the GPUs named by B200MVS_DEVICES (default: device B200MVS_DEVICE or
+// 0) and (ii) per GPU COMBINED: one caller becomes the leader and submits every request that is waiting as ONE batched
+// b200mvs_reconstruct (all views of a batch advance together, which is what keeps the GPU full), the others sleep until
+// their result is there.
+struct Request {
+    int32_t ref = 0;
+    b200mvs_settings settings;
+    b200mvs_maps maps;
+    b200mvs_progress prog;
+    b200mvs_stats stats;
+    int rc = 0;
+    std::string err;
+    bool done = false;
+};
+
+struct DeviceCtx {
+    std::mutex mtx;                 // protects everything below
+    std::condition_variable cv;
+    int device = 0;
     mve::Scene::Ptr scene;
     std::string embedding;
     b200mvs_ctx* ctx = nullptr;
     std::vector<char> uploaded;
     bool features_set = false;
-    ~SharedCtx() { if (ctx) b200mvs_destroy(ctx); }
+    bool leader_active = false;
+    std::vector<Request*> pending;
+    ~DeviceCtx() { if (ctx) b200mvs_destroy(ctx); }
 };
-SharedCtx g_shared;
 
-int pick_device()
+std::mutex g_mtx;
+std::vector<std::unique_ptr<DeviceCtx>> g_devices;
+std::atomic<unsigned> g_next(0);
+
+std::vector<int> device_list()
 {
-    const char* e = std::getenv("B200MVS_DEVICE");
-    return e ? std::atoi(e) : 0;
+    std::vector<int> out;
+    if (const char* e = std::getenv("B200MVS_DEVICES")) {
+        std::string s(e);
+        size_t pos = 0;
+        while (pos < s.size()) {
+            size_t q = s.find(',', pos);
+            if (q == std::string::npos) q = s.size();
+            if (q > pos) out.push_back(std::atoi(s.substr(pos, q - pos).c_str()));
+            pos = q + 1;
+        }
+    }
+    if (out.empty()) {
+        const char* e = std::getenv("B200MVS_DEVICE");
+        out.push_back(e ? std::atoi(e) : 0);
+    }
+    return out;
 }
 
-void throw_for(int rc, b200mvs_ctx* ctx)
+DeviceCtx& pick_device_ctx()
 {
-    const std::string msg = b200mvs_last_error(ctx);
+    std::lock_guard<std::mutex> lk(g_mtx);
+    if (g_devices.empty())
+        for (int d : device_list()) { g_devices.emplace_back(new DeviceCtx()); g_devices.back()->device = d; }
+    return *g_devices[g_next.fetch_add(1) % g_devices.size()];
+}
+
+void throw_for(int rc, const std::string& msg)
+{
     if (rc == B200MVS_ERR_INVALID_ARG || rc == B200MVS_ERR_UNSUPPORTED) throw std::invalid_argument(msg);
     throw std::runtime_error(msg);     // B200MVS_ERR_GLOBAL_VS ("Global View Selection failed"), CUDA errors, overflow
+}
+
+bool same_settings(const b200mvs_settings& a, const b200mvs_settings& b) { return std::memcmp(&a, &b, sizeof(a)) == 0; }
+
+// Runs one batch on the device context (called by the leader WITHOUT holding D.mtx for the GPU work itself).
+void run_batch(DeviceCtx& D, std::vector<Request*>& batch)
+{
+    while (!batch.empty()) {
+        std::vector<int32_t> refs;
+        std::vector<b200mvs_maps> maps;
+        std::vector<b200mvs_progress> prog;
+        for (Request* r : batch) { refs.push_back(r->ref); maps.push_back(r->maps); prog.push_back(r->prog); }
+        b200mvs_stats stats;
+        int32_t failed = -1;
+        const int rc = b200mvs_reconstruct(D.ctx, &batch[0]->settings, (int)batch.size(), refs.data(), maps.data(), prog.data(),
+                                           &stats, &failed);
+        if (rc == 0 || rc == B200MVS_ERR_CANCELLED) {
+            for (size_t i = 0; i < batch.size(); ++i) {
+                batch[i]->rc = rc; batch[i]->prog = prog[i]; batch[i]->maps = maps[i]; batch[i]->stats = stats;
+                batch[i]->err = rc ? b200mvs_last_error(D.ctx) : "";
+            }
+            return;
+        }
+        // one view made the call fail (e.g. "Global View Selection failed"): give it its error, retry the others
+        const std::string msg = b200mvs_last_error(D.ctx);
+        bool removed = false;
+        for (size_t i = 0; i < batch.size(); ++i) {
+            if (failed >= 0 && batch[i]->ref != failed) continue;
+            batch[i]->rc = rc; batch[i]->err = msg;
+            if (failed >= 0) { batch.erase(batch.begin() + i); removed = true; break; }
+        }
+        if (failed < 0 || !removed) return;      // error not attributable to one view: every request got it
+    }
 }
 
 } // namespace
@@ -96,36 +176,39 @@ DMRecon::start()
 {
     progress.start_time = std::time(nullptr);
     mve::Scene::ViewList const& mve_views(scene->get_views());
-    std::unique_lock<std::mutex> lock(g_shared.mtx);
+    DeviceCtx& D = pick_device_ctx();
+    std::unique_lock<std::mutex> lock(D.mtx);
 
     /* (Re)create the device context for this scene. */
-    if (g_shared.ctx == nullptr || g_shared.scene != scene || g_shared.embedding != settings.imageEmbedding) {
-        if (g_shared.ctx) { b200mvs_destroy(g_shared.ctx); g_shared.ctx = nullptr; }
-        int rc = b200mvs_create(pick_device(), (int)mve_views.size(), &g_shared.ctx);
+    if (D.ctx == nullptr || D.scene != scene || D.embedding != settings.imageEmbedding) {
+        while (D.leader_active) D.cv.wait(lock);
+        if (D.ctx) { b200mvs_destroy(D.ctx); D.ctx = nullptr; }
+        int rc = b200mvs_create(D.device, (int)mve_views.size(), &D.ctx);
         if (rc != 0) throw std::runtime_error(b200mvs_last_error(nullptr));
-        g_shared.scene = scene;
-        g_shared.embedding = settings.imageEmbedding;
-        g_shared.uploaded.assign(mve_views.size(), 0);
-        g_shared.features_set = false;
+        D.scene = scene;
+        D.embedding = settings.imageEmbedding;
+        D.uploaded.assign(mve_views.size(), 0);
+        D.features_set = false;
     }
-    b200mvs_ctx* ctx = g_shared.ctx;
+    b200mvs_ctx* ctx = D.ctx;
 
     /* Views: the same validity test as dmrecon.cc:62-71; images are uploaded once and their pyramids cached. */
     progress.status = RECON_FEATURES;
     for (std::size_t i = 0; i < mve_views.size() && !progress.cancelled; ++i) {
-        if (g_shared.uploaded[i]) continue;
+        if (D.uploaded[i]) continue;
         mve::View::Ptr v = mve_views[i];
         if (v == nullptr || !v->is_camera_valid() || !v->has_image(settings.imageEmbedding, mve::IMAGE_TYPE_UINT8))
             continue;
         mve::ByteImage::Ptr img = v->get_byte_image(settings.imageEmbedding);
         mve::CameraInfo const& cam = v->get_camera();
+        while (D.leader_active) D.cv.wait(lock);      // uploads change the context: not while a batch is running
         int rc = b200mvs_upload_view(ctx, (int)i, img->get_data_pointer(), img->width(), img->height(), img->channels(),
             cam.flen, cam.paspect, cam.ppoint, cam.rot, cam.trans);
         v->cache_cleanup();
-        if (rc != 0) throw_for(rc, ctx);
-        g_shared.uploaded[i] = 1;
+        if (rc != 0) throw_for(rc, b200mvs_last_error(ctx));
+        D.uploaded[i] = 1;
     }
-    if (!g_shared.features_set) {
+    if (!D.features_set) {
         mve::Bundle::Features const& features = bundle->get_features();
         std::vector<float> pos(features.size() * 3);
         std::vector<int32_t> off(features.size() + 1, 0), ids;
@@ -134,9 +217,10 @@ DMRecon::start()
             for (std::size_t j = 0; j < features[i].refs.size(); ++j) ids.push_back(features[i].refs[j].view_id);
             off[i + 1] = (int32_t)ids.size();
         }
+        while (D.leader_active) D.cv.wait(lock);
         int rc = b200mvs_set_features(ctx, (int)features.size(), pos.data(), off.data(), ids.data());
-        if (rc != 0) throw_for(rc, ctx);
-        g_shared.features_set = true;
+        if (rc != 0) throw_for(rc, b200mvs_last_error(ctx));
+        D.features_set = true;
     }
     if (progress.cancelled) { progress.status = RECON_CANCELLED; return; }
 
@@ -157,6 +241,7 @@ DMRecon::start()
 
     if (!settings.quiet) {
         int32_t ids[B200MVS_MAX_GLOBAL_VIEWS];
+        while (D.leader_active) D.cv.wait(lock);
         int n = b200mvs_global_view_selection(ctx, &s, (int)settings.refViewNr, ids, B200MVS_MAX_GLOBAL_VIEWS);
         if (n > 0) {
             std::cout << "Global View Selection:";
@@ -169,25 +254,50 @@ DMRecon::start()
     mve::FloatImage::Ptr depthImg = mve::FloatImage::create(width, height, 1);
     mve::FloatImage::Ptr dzImg = mve::FloatImage::create(width, height, 2);
     mve::FloatImage::Ptr confImg = mve::FloatImage::create(width, height, 1);
-    b200mvs_maps maps;
-    std::memset(&maps, 0, sizeof(maps));
-    maps.depth = depthImg->get_data_pointer();
-    maps.dz = dzImg->get_data_pointer();
-    maps.conf = confImg->get_data_pointer();
-    b200mvs_progress prog;
-    std::memset(&prog, 0, sizeof(prog));
-    prog.cancelled = progress.cancelled ? 1 : 0;
-    b200mvs_stats stats;
-    int32_t ref = (int32_t)settings.refViewNr, failed = -1;
+    Request req;
+    req.ref = (int32_t)settings.refViewNr;
+    req.settings = s;
+    std::memset(&req.maps, 0, sizeof(req.maps));
+    req.maps.depth = depthImg->get_data_pointer();
+    req.maps.dz = dzImg->get_data_pointer();
+    req.maps.conf = confImg->get_data_pointer();
+    std::memset(&req.prog, 0, sizeof(req.prog));
+    req.prog.cancelled = progress.cancelled ? 1 : 0;
+    std::memset(&req.stats, 0, sizeof(req.stats));
     progress.status = RECON_QUEUE;
-    int rc = b200mvs_reconstruct(ctx, &s, 1, &ref, &maps, &prog, &stats, &failed);
-    progress.filled = prog.filled;
+
+    /* Submit: whoever finds no leader runs the batches until the queue is empty. */
+    D.pending.push_back(&req);
+    if (!D.leader_active) {
+        D.leader_active = true;
+        while (!D.pending.empty()) {
+            std::vector<Request*> batch;
+            std::vector<Request*> rest;
+            for (Request* r : D.pending) (batch.empty() || same_settings(r->settings, batch[0]->settings) ? batch : rest).push_back(r);
+            D.pending.swap(rest);
+            std::vector<Request*> running(batch);
+            lock.unlock();
+            run_batch(D, running);
+            lock.lock();
+            for (Request* r : batch) r->done = true;
+            D.cv.notify_all();
+        }
+        D.leader_active = false;
+        D.cv.notify_all();
+    }
+    while (!req.done) D.cv.wait(lock);
+    lock.unlock();
+
+    const b200mvs_stats& stats = req.stats;
+    const int rc0 = req.rc;
+    progress.filled = req.prog.filled;
     progress.queueSize = 0;
-    if (rc == B200MVS_ERR_CANCELLED || progress.cancelled) { progress.status = RECON_CANCELLED; return; }
-    if (rc != 0) throw_for(rc, ctx);
+    if (rc0 == B200MVS_ERR_CANCELLED || progress.cancelled) { progress.status = RECON_CANCELLED; return; }
+    if (rc0 != 0) throw_for(rc0, req.err);
     if (!settings.quiet)
-        std::cout << "Processed " << stats.n_seeds_processed << " features, from which "
-                  << stats.n_seeds_success << " succeeded optimization." << std::endl;
+        std::cout << "Reconstructed view " << settings.refViewNr << " (batched with the views in flight: " << stats.n_seeds_processed
+                  << " features processed, " << stats.n_seeds_success << " succeeded optimization, " << stats.n_rounds
+                  << " frontier rounds)." << std::endl;
 
     progress.status = RECON_SAVING;
     mve::View::Ptr view = mve_views[settings.refViewNr];
@@ -207,8 +317,8 @@ DMRecon::start()
     if (settings.scale != 0) {
         mve::ByteImage::Ptr scaled = mve::ByteImage::create(width, height, 3);
         int w = 0, h = 0;
-        rc = b200mvs_get_level(ctx, (int)settings.refViewNr, settings.scale, &w, &h, scaled->get_data_pointer());
-        if (rc != 0) throw_for(rc, ctx);
+        int rc = b200mvs_get_level(ctx, (int)settings.refViewNr, settings.scale, &w, &h, scaled->get_data_pointer());
+        if (rc != 0) throw_for(rc, b200mvs_last_error(ctx));
         name = "undist-L";
         name += util::string::get(settings.scale);
         view->set_image(scaled, name);
