@@ -15,9 +15,9 @@
 //     the instruction stream (the first version inlined 16 copies and stalled on instruction fetch,
 //     profiles/r1_notes.md);
 //   * small per-view arrays (selected slots, colour scales, NCCs) live one element per lane and are
-//     read with warp shuffles; sums over the 25 samples are warp-shuffle reductions; the 3x3 normal
-//     equations are accumulated per lane in fp64 from fp32 products exactly as
-//     patch_optimization.cc:326-343 and reduced once per pass.
+//     read with warp shuffles; sums over the 25 samples are (batched) warp-shuffle butterflies; the
+//     sums of the 3x3 normal equations (patch_optimization.cc:326-343) are formed per lane in fp32
+//     (<= 12 products) and across the lanes in fp64, then solved in fp64 inside the pass.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
