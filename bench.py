@@ -45,6 +45,7 @@ def workload_cfg(name, n_gpus):
     if name == "C2" and n_gpus > 1:
         cfg["views"] = VIEWS_PER_GPU * n_gpus
         cfg["grid"] = (4 * n_gpus, 4)
+        cfg["blocks"] = n_gpus            # N copies of the 4x4 camera block side by side; rank r owns block r
         cfg["features"] = 4000 * n_gpus
     cfg["name"] = name
     return cfg

@@ -185,14 +185,20 @@ def make_scene(config, device: Optional[str] = None, only_views=None, **override
         gx, gy = cfg["grid"]
         assert gx * gy == V
         p = cfg["pitch"]
-        for j in range(gy):
-            for i in range(gx):
-                c = np.array([(i - (gx - 1) / 2) * p, (j - (gy - 1) / 2) * p,
-                              -dist * (1.0 + rng.uniform(-0.07, 0.07))])
-                # converge mildly towards the scene centre
-                tgt = np.array([c[0] * 0.35, c[1] * 0.35, 0.0])
-                cams_pos.append(c)
-                cams_rot.append(_look_at(c, tgt))
+        # `blocks` > 1 tiles the scene along x with identical gx/blocks x gy camera blocks (weak scaling: every block has
+        # the geometry of the single-block scene, view ids are block-major so that rank r owns block r)
+        nb = cfg.get("blocks", 1)
+        bx = gx // nb
+        for b in range(nb):
+            for j in range(gy):
+                for i in range(bx):
+                    lx, ly = (i - (bx - 1) / 2) * p, (j - (gy - 1) / 2) * p        # position inside the block
+                    c = np.array([lx + b * bx * p - (nb - 1) * bx * p / 2, ly,
+                                  -dist * (1.0 + rng.uniform(-0.07, 0.07))])
+                    # converge mildly towards the centre of the camera's own block
+                    tgt = np.array([c[0] - 0.65 * lx, c[1] - 0.65 * ly, 0.0])
+                    cams_pos.append(c)
+                    cams_rot.append(_look_at(c, tgt))
     elif cfg["layout"] == "orbit":
         per_ring = cfg.get("orbit_views_per_ring", V // 2)
         rings = V // per_ring
@@ -246,23 +252,21 @@ def make_scene(config, device: Optional[str] = None, only_views=None, **override
         p = np.concatenate([xy, z[:, None]], 1)
         nrm = None
     feat_pos = p.astype(np.float32)
-    feat_refs = []
-    for f in range(F):
-        ids = []
-        X = feat_pos[f].astype(np.float64)
-        for v in range(V):
-            Rm = rot32[v].astype(np.float64).reshape(3, 3)
-            cp = Rm @ X + trans32[v].astype(np.float64)
-            if cp[2] <= 0:
-                continue
-            x = ax * cp[0] / cp[2] + 0.5 * W - 0.5
-            y = ax * cp[1] / cp[2] + 0.5 * H - 0.5
-            if not (1.0 <= x <= W - 2 and 1.0 <= y <= H - 2):
-                continue
-            if nrm is not None and float(nrm[f] @ (pos[v] - X)) / np.linalg.norm(pos[v] - X) < 0.35:
-                continue
-            ids.append(v)
-        feat_refs.append(np.asarray(ids, dtype=np.int32))
+    X = feat_pos.astype(np.float64)                                   # [F, 3]
+    vis = np.zeros((len(X), V), dtype=bool)
+    for v in range(V):
+        Rm = rot32[v].astype(np.float64).reshape(3, 3)
+        cp = X @ Rm.T + trans32[v].astype(np.float64)                 # [F, 3]
+        z = cp[:, 2]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            x = ax * cp[:, 0] / z + 0.5 * W - 0.5
+            y = ax * cp[:, 1] / z + 0.5 * H - 0.5
+        ok = (z > 0) & (x >= 1.0) & (x <= W - 2) & (y >= 1.0) & (y <= H - 2)
+        if nrm is not None:
+            to_cam = pos[v] - X
+            ok &= (np.einsum("ij,ij->i", nrm, to_cam) / np.linalg.norm(to_cam, axis=1)) >= 0.35
+        vis[:, v] = ok
+    feat_refs = [np.nonzero(vis[f])[0].astype(np.int32) for f in range(len(X))]
     keep = [i for i, r in enumerate(feat_refs) if len(r) >= 2]
     feat_pos = feat_pos[keep]
     feat_refs = [feat_refs[i] for i in keep]
