@@ -244,12 +244,22 @@ def _main(real_stdout):
     gscene = dmrecon.Scene(scene.n_views, device=local)
     gscene.set_features(scene.feat_pos, scene.feat_refs)
 
+    # Cameras of every view are registered once; like the reference (dmrecon.cc:78,238-240) only the images of this rank's
+    # reference views and of their selected neighbours are turned into pyramids on this GPU.
+    for v in range(scene.n_views):
+        gscene.set_view_camera(v, W, H, scene.flen[v], scene.paspect[v], scene.ppoint[v], scene.rot[v], scene.trans[v])
+    needed = set(owned)
+    for r in owned:
+        needed.update(gscene.global_view_selection(settings, r))
+    needed = sorted(needed)
+    log("[rank %d] %d of %d views needed on this GPU" % (rank, len(needed), scene.n_views))
+
     def upload_all():
-        """pinned host -> device for the owned views, all-gather of the image shards, pyramids on device."""
+        """pinned host -> device for the owned views, all-gather of the image shards, pyramids of the needed views."""
         dimgs = host_imgs.to(dev, non_blocking=True)
         all_imgs = sharding.all_gather_images(dimgs, world)          # [V, H, W, 3] on every rank
         torch.cuda.synchronize()
-        for v in range(scene.n_views):
+        for v in needed:
             gscene.set_view_device(v, all_imgs[v].data_ptr(), W, H, scene.flen[v], scene.paspect[v], scene.ppoint[v],
                                    scene.rot[v], scene.trans[v])
         return all_imgs

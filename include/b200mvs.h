@@ -136,6 +136,13 @@ int b200mvs_upload_view(b200mvs_ctx* ctx, int view_id, const uint8_t* rgb, int w
 int b200mvs_upload_view_device(b200mvs_ctx* ctx, int view_id, const uint8_t* rgb_dev, int w, int h,
                                float flen, float paspect, const float ppoint[2],
                                const float rot[9], const float trans[3], void* cuda_stream);
+/* Camera and image size only - SingleView::create (single_view.cc:24-53).  The reference creates a SingleView for every
+ * valid view but loads colour images only for the master view and its selected neighbours (dmrecon.cc:78,238-240); a
+ * caller that wants the same economy registers all cameras, asks b200mvs_global_view_selection which views are needed
+ * and uploads only those images.  b200mvs_reconstruct fails with B200MVS_ERR_INVALID_ARG ("color image of view N is not
+ * loaded") when a needed image is missing. */
+int b200mvs_set_view_camera(b200mvs_ctx* ctx, int view_id, int w, int h, float flen, float paspect,
+                            const float ppoint[2], const float rot[9], const float trans[3]);
 /* mve::Bundle::Features (bundle.h:51-60) as position + CSR list of referencing view ids. */
 int b200mvs_set_features(b200mvs_ctx* ctx, int n_features, const float* pos,
                          const int32_t* ref_offsets, const int32_t* ref_view_ids);

@@ -31,7 +31,8 @@ struct HostLevel {
 };
 
 struct HostView {
-    bool valid = false;
+    bool valid = false;            // a SingleView exists (camera + image dimensions known)
+    bool has_image = false;        // loadColorImage done: pyramid resident on the device
     int w = 0, h = 0;
     float flen = 0, paspect = 1, pp[2] = {0.5f, 0.5f}, rot[9], trans[3];
     float campos[3];
@@ -591,6 +592,7 @@ int upload_common(b200mvs_ctx* ctx, int id, const uint8_t* d_src, int w, int h, 
 {
     HostView& v = ctx->views[id];
     v.valid = false;
+    v.has_image = false;
     v.w = w; v.h = h; v.flen = flen; v.paspect = paspect; v.pp[0] = pp[0]; v.pp[1] = pp[1];
     std::memcpy(v.rot, rot, sizeof(v.rot));
     std::memcpy(v.trans, trans, sizeof(v.trans));
@@ -618,6 +620,14 @@ int upload_common(b200mvs_ctx* ctx, int id, const uint8_t* d_src, int w, int h, 
         push_level();
     }
     if ((int)v.lv.size() > MAX_LEVELS) return fail(ctx, B200MVS_ERR_UNSUPPORTED, "image too large: %d pyramid levels", (int)v.lv.size());
+    if (!d_src) {
+        // camera only (SingleView::create, single_view.cc:24-53): the image follows with an upload if the view turns out
+        // to be a reference view or a selected neighbour (loadColorImage, dmrecon.cc:78,238-240)
+        if (v.d_base) { cudaFree(v.d_base); v.d_base = nullptr; v.bytes = 0; }
+        v.valid = true;
+        ctx->views_dirty = true;
+        return 0;
+    }
     size_t total = 0;
     for (HostLevel& L : v.lv) total += (size_t)L.pitch * L.h;
     if (!v.d_base || v.bytes != total * sizeof(uchar4)) {
@@ -639,6 +649,7 @@ int upload_common(b200mvs_ctx* ctx, int id, const uint8_t* d_src, int w, int h, 
     }
     CK(cudaGetLastError());
     v.valid = true;
+    v.has_image = true;
     ctx->views_dirty = true;
     return 0;
 }
@@ -661,7 +672,7 @@ int sync_view_params(b200mvs_ctx* ctx)
         for (size_t l = 0; l < v.lv.size(); ++l) {
             const HostLevel& L = v.lv[l];
             p.lv[l].ax = L.proj[0]; p.lv[l].ay = L.proj[4]; p.lv[l].cx = L.proj[2]; p.lv[l].cy = L.proj[5];
-            p.lv[l].w = L.w; p.lv[l].h = L.h; p.lv[l].pitch = L.pitch; p.lv[l].img = L.d_img;
+            p.lv[l].w = L.w; p.lv[l].h = L.h; p.lv[l].pitch = L.pitch; p.lv[l].img = v.has_image ? L.d_img : nullptr;
         }
     }
     CK(cudaMemcpyAsync(ctx->d_views, hp.data(), hp.size() * sizeof(ViewParams), cudaMemcpyHostToDevice, ctx->stream));
@@ -813,6 +824,17 @@ int b200mvs_upload_view_device(b200mvs_ctx* ctx, int id, const uint8_t* rgb_dev,
     return rc;
 }
 
+int b200mvs_set_view_camera(b200mvs_ctx* ctx, int id, int w, int h, float flen, float paspect, const float ppoint[2],
+                            const float rot[9], const float trans[3])
+{
+    if (!ctx) return B200MVS_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mtx);
+    if (id < 0 || id >= (int)ctx->views.size() || w < 2 || h < 2 || !ppoint || !rot || !trans)
+        return fail(ctx, B200MVS_ERR_INVALID_ARG, "b200mvs_set_view_camera: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    return upload_common(ctx, id, nullptr, w, h, 3, flen, paspect, ppoint, rot, trans, ctx->stream);
+}
+
 int b200mvs_set_features(b200mvs_ctx* ctx, int n, const float* pos, const int32_t* off, const int32_t* ids)
 {
     if (!ctx) return B200MVS_ERR_INVALID_ARG;
@@ -843,6 +865,7 @@ int b200mvs_get_level(b200mvs_ctx* ctx, int id, int level, int* w, int* h, uint8
     if (w) *w = L.w;
     if (h) *h = L.h;
     if (!rgb) return 0;
+    if (!v.has_image) return fail(ctx, B200MVS_ERR_INVALID_ARG, "color image of view %d is not loaded", id);
     CK(cudaSetDevice(ctx->device));
     uint8_t* d = nullptr;
     CK(cudaMalloc(&d, (size_t)L.w * L.h * 3));
@@ -882,6 +905,8 @@ int b200mvs_optimize_patches(b200mvs_ctx* ctx, const b200mvs_settings* s, int re
     std::vector<int> gsel(gids, gids + ng);
     if (!std::is_sorted(gsel.begin(), gsel.end())) return fail(ctx, B200MVS_ERR_INVALID_ARG, "global ids must be ascending");
     for (int g : gsel) if (g < 0 || g >= (int)ctx->views.size() || !ctx->views[g].valid) return fail(ctx, B200MVS_ERR_INVALID_ARG, "invalid global view id");
+    if (!ctx->views[ref].has_image) return fail(ctx, B200MVS_ERR_INVALID_ARG, "color image of view %d is not loaded", ref);
+    for (int g : gsel) if (!ctx->views[g].has_image) return fail(ctx, B200MVS_ERR_INVALID_ARG, "color image of view %d is not loaded", g);
     if (stats) std::memset(stats, 0, sizeof(*stats));
     if (n == 0) return 0;
     CK(cudaSetDevice(ctx->device));
@@ -1004,6 +1029,9 @@ int b200mvs_reconstruct(b200mvs_ctx* ctx, const b200mvs_settings* s, int n_refs,
             if (failed_view) *failed_view = refs[j];
             return fail(ctx, B200MVS_ERR_GLOBAL_VS, "Global View Selection failed");
         }
+        if (!ctx->views[refs[j]].has_image) { if (failed_view) *failed_view = refs[j]; return fail(ctx, B200MVS_ERR_INVALID_ARG, "color image of view %d is not loaded", refs[j]); }
+        for (int g : gsels[j])
+            if (!ctx->views[g].has_image) { if (failed_view) *failed_view = refs[j]; return fail(ctx, B200MVS_ERR_INVALID_ARG, "color image of view %d (selected neighbour of view %d) is not loaded", g, refs[j]); }
         if ((rc = make_job(ctx, *s, refs[j], gsels[j], jobs[j]))) return rc;
         px_off[j] = total_px;
         total_px += (size_t)jobs[j].W * jobs[j].H;

@@ -74,7 +74,7 @@ PATCH_OUT = np.dtype([("conf", "<f4"), ("depth", "<f4"), ("dz_i", "<f4"), ("dz_j
                       ("iterations", "<i4"), ("converged", "<i4"), ("opti_success", "<i4")])
 
 EXPORTS = ["b200mvs_default_settings", "b200mvs_create", "b200mvs_destroy", "b200mvs_last_error", "b200mvs_version",
-           "b200mvs_upload_view", "b200mvs_upload_view_device", "b200mvs_set_features", "b200mvs_num_levels",
+           "b200mvs_upload_view", "b200mvs_upload_view_device", "b200mvs_set_view_camera", "b200mvs_set_features", "b200mvs_num_levels",
            "b200mvs_get_level", "b200mvs_global_view_selection", "b200mvs_optimize_patches", "b200mvs_reconstruct"]
 
 
@@ -98,6 +98,7 @@ def lib():
     L.b200mvs_upload_view_device.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float,
                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.b200mvs_set_features.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.b200mvs_set_view_camera.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
     L.b200mvs_num_levels.argtypes = [C.c_void_p, C.c_int]
     L.b200mvs_get_level.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     L.b200mvs_global_view_selection.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
@@ -170,6 +171,13 @@ class Scene:
         t = np.ascontiguousarray(trans, np.float32).reshape(3)
         self._check(self._lib.b200mvs_upload_view_device(self._h, view_id, C.c_void_p(dev_ptr), w, h, float(flen),
                                                          float(paspect), _p(pp), _p(r), _p(t), C.c_void_p(stream)))
+
+    def set_view_camera(self, view_id: int, w: int, h: int, flen, paspect, ppoint, rot, trans):
+        """SingleView::create: camera + image size, the colour image is loaded later (or never, if not needed)."""
+        pp = np.ascontiguousarray(ppoint, np.float32)
+        r = np.ascontiguousarray(rot, np.float32).reshape(9)
+        t = np.ascontiguousarray(trans, np.float32).reshape(3)
+        self._check(self._lib.b200mvs_set_view_camera(self._h, view_id, w, h, float(flen), float(paspect), _p(pp), _p(r), _p(t)))
 
     def set_features(self, pos: np.ndarray, refs: Sequence[np.ndarray]):
         """mve::Bundle::Features (bundle.h:51-60)."""

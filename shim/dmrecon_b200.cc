@@ -61,6 +61,7 @@ struct DeviceCtx {
     b200mvs_ctx* ctx = nullptr;
     std::vector<char> uploaded;
     bool features_set = false;
+    bool cameras_set = false;
     bool leader_active = false;
     std::vector<Request*> pending;
     ~DeviceCtx() { if (ctx) b200mvs_destroy(ctx); }
@@ -189,24 +190,27 @@ DMRecon::start()
         D.embedding = settings.imageEmbedding;
         D.uploaded.assign(mve_views.size(), 0);
         D.features_set = false;
+        D.cameras_set = false;
     }
     b200mvs_ctx* ctx = D.ctx;
 
-    /* Views: the same validity test as dmrecon.cc:62-71; images are uploaded once and their pyramids cached. */
+    /* Views: the same validity test as dmrecon.cc:62-71.  Every valid view gets its camera registered
+       (SingleView::create); colour images are loaded further down, only for the master view and its selected
+       neighbours (loadColorImage, dmrecon.cc:78,238-240), once per view and context. */
     progress.status = RECON_FEATURES;
-    for (std::size_t i = 0; i < mve_views.size() && !progress.cancelled; ++i) {
-        if (D.uploaded[i]) continue;
-        mve::View::Ptr v = mve_views[i];
-        if (v == nullptr || !v->is_camera_valid() || !v->has_image(settings.imageEmbedding, mve::IMAGE_TYPE_UINT8))
-            continue;
-        mve::ByteImage::Ptr img = v->get_byte_image(settings.imageEmbedding);
-        mve::CameraInfo const& cam = v->get_camera();
-        while (D.leader_active) D.cv.wait(lock);      // uploads change the context: not while a batch is running
-        int rc = b200mvs_upload_view(ctx, (int)i, img->get_data_pointer(), img->width(), img->height(), img->channels(),
-            cam.flen, cam.paspect, cam.ppoint, cam.rot, cam.trans);
-        v->cache_cleanup();
-        if (rc != 0) throw_for(rc, b200mvs_last_error(ctx));
-        D.uploaded[i] = 1;
+    if (!D.cameras_set) {
+        while (D.leader_active) D.cv.wait(lock);
+        for (std::size_t i = 0; i < mve_views.size(); ++i) {
+            mve::View::Ptr v = mve_views[i];
+            if (v == nullptr || !v->is_camera_valid() || !v->has_image(settings.imageEmbedding, mve::IMAGE_TYPE_UINT8))
+                continue;
+            mve::View::ImageProxy const* proxy = v->get_image_proxy(settings.imageEmbedding);
+            mve::CameraInfo const& cam = v->get_camera();
+            int rc = b200mvs_set_view_camera(ctx, (int)i, proxy->width, proxy->height, cam.flen, cam.paspect, cam.ppoint,
+                cam.rot, cam.trans);
+            if (rc != 0) throw_for(rc, b200mvs_last_error(ctx));
+        }
+        D.cameras_set = true;
     }
     if (!D.features_set) {
         mve::Bundle::Features const& features = bundle->get_features();
@@ -239,16 +243,36 @@ DMRecon::start()
     s.use_color_scale = settings.useColorScale ? 1 : 0;
     for (int i = 0; i < 3; ++i) { s.aabb_min[i] = settings.aabbMin[i]; s.aabb_max[i] = settings.aabbMax[i]; }
 
-    if (!settings.quiet) {
+    /* globalViewSelection (dmrecon.cc:211-241) decides which colour images are needed. */
+    progress.status = RECON_GLOBALVS;
+    {
         int32_t ids[B200MVS_MAX_GLOBAL_VIEWS];
         while (D.leader_active) D.cv.wait(lock);
         int n = b200mvs_global_view_selection(ctx, &s, (int)settings.refViewNr, ids, B200MVS_MAX_GLOBAL_VIEWS);
-        if (n > 0) {
+        if (n < 0) throw_for(n, b200mvs_last_error(ctx));
+        if (n == 0) throw std::runtime_error("Global View Selection failed");
+        if (!settings.quiet) {
             std::cout << "Global View Selection:";
             for (int i = 0; i < n; ++i) std::cout << " " << ids[i];
-            std::cout << std::endl;
+            std::cout << std::endl << "Loading color images..." << std::endl;
+        }
+        std::vector<int> need(ids, ids + n);
+        need.push_back((int)settings.refViewNr);
+        for (int id : need) {
+            if (progress.cancelled) break;
+            if (D.uploaded[id]) continue;
+            mve::View::Ptr v = mve_views[id];
+            mve::ByteImage::Ptr img = v->get_byte_image(settings.imageEmbedding);
+            mve::CameraInfo const& cam = v->get_camera();
+            while (D.leader_active) D.cv.wait(lock);      // uploads change the context: not while a batch is running
+            int rc = b200mvs_upload_view(ctx, id, img->get_data_pointer(), img->width(), img->height(), img->channels(),
+                cam.flen, cam.paspect, cam.ppoint, cam.rot, cam.trans);
+            v->cache_cleanup();
+            if (rc != 0) throw_for(rc, b200mvs_last_error(ctx));
+            D.uploaded[id] = 1;
         }
     }
+    if (progress.cancelled) { progress.status = RECON_CANCELLED; return; }
 
     /* Result images, allocated like SingleView::prepareMasterView (single_view.cc:78-81). */
     mve::FloatImage::Ptr depthImg = mve::FloatImage::create(width, height, 1);

@@ -152,6 +152,35 @@ def test_error_behaviour():
     assert int(st.n_filled) == 0 and not (maps[0]["depth"] > 0).any()
 
 
+def test_camera_only_views_and_missing_images():
+    """SingleView::create vs loadColorImage: cameras of all views, images only where needed (dmrecon.cc:78,238-240)."""
+    from mve_b200 import dmrecon
+    s = golden_scene("T3")          # 40 views, 20 selected
+    st = dmrecon.Settings()
+    full = dmrecon.Scene.from_synth(s)
+    ref = 7
+    want, _ = full.reconstruct(st, [ref])
+    g = dmrecon.Scene(s.n_views)
+    for v in range(s.n_views):
+        g.set_view_camera(v, s.width, s.height, s.flen[v], s.paspect[v], s.ppoint[v], s.rot[v], s.trans[v])
+    g.set_features(s.feat_pos, s.feat_refs)
+    sel = g.global_view_selection(st, ref)
+    assert sel == full.global_view_selection(st, ref) and len(sel) == 20
+    with pytest.raises(dmrecon.B200MVSError) as e:
+        g.reconstruct(st, [ref])
+    assert e.value.code == -1 and "not loaded" in str(e.value)
+    for v in [ref] + sel[:-1]:
+        g.set_view(v, s.images[v], s.flen[v], s.paspect[v], s.ppoint[v], s.rot[v], s.trans[v])
+    with pytest.raises(dmrecon.B200MVSError) as e:
+        g.reconstruct(st, [ref])
+    assert "selected neighbour" in str(e.value)
+    v = sel[-1]
+    g.set_view(v, s.images[v], s.flen[v], s.paspect[v], s.ppoint[v], s.rot[v], s.trans[v])
+    got, _ = g.reconstruct(st, [ref])
+    for k in ("depth", "conf", "dz", "view_ids"):
+        assert (got[0][k] == want[0][k]).all()
+
+
 def test_cancel():
     """Progress::cancelled is polled once per frontier round (dmrecon.cc:353) -> B200MVS_ERR_CANCELLED."""
     from mve_b200 import dmrecon
