@@ -118,6 +118,10 @@ typedef struct b200mvs_stats {
 } b200mvs_stats;
 
 /* ---- lifecycle (mvs::DMRecon ctor/dtor, dmrecon.cc:30-87; ImagePyramidCache, image_pyramid.cc:99-160) ---- */
+/* device >= 0: a CUDA device (fails loudly when there is none).  B200MVS_DEVICE_NONE creates a PLANNING context without a
+ * GPU: b200mvs_set_view_camera, b200mvs_set_features and b200mvs_global_view_selection work (they are host logic in the
+ * reference too); every entry point that computes on images fails with B200MVS_ERR_CUDA - there is no CPU fallback. */
+#define B200MVS_DEVICE_NONE (-1)
 int  b200mvs_create(int device, int n_views, b200mvs_ctx** out);
 void b200mvs_destroy(b200mvs_ctx* ctx);
 const char* b200mvs_last_error(const b200mvs_ctx* ctx);   /* ctx may be NULL: last create() error */

@@ -82,6 +82,7 @@ struct b200mvs_ctx {
     std::string err;
     std::vector<HostView> views;
     std::vector<HostFeature> feats;
+    std::vector<std::vector<int>> view_feats;   // inverted index: ascending ids of the features that reference a view
     ViewParams* d_views = nullptr;
     bool views_dirty = true;
     float* d_lut = nullptr;
@@ -186,9 +187,10 @@ std::vector<int> global_view_selection(const b200mvs_ctx* c, const b200mvs_setti
     const int nv = (int)c->views.size();
     const HostView& rv = c->views[ref];
     std::vector<std::vector<int>> featInd(nv);
-    for (size_t i = 0; i < c->feats.size(); ++i) {
+    static const std::vector<int> no_feats;
+    const std::vector<int>& of_ref = ref < (int)c->view_feats.size() ? c->view_feats[ref] : no_feats;
+    for (int i : of_ref) {                       // the features with contains_view_id(refViewNr), ascending (dmrecon.cc:186-188)
         const HostFeature& f = c->feats[i];
-        if (!feature_has_view(f, ref)) continue;
         if (!point_in_frustum(rv, f.pos)) continue;
         if (!in_aabb(f.pos, st)) continue;
         for (int vid : f.refs) {
@@ -301,10 +303,14 @@ std::vector<Seed> collect_seeds(const b200mvs_ctx* c, const b200mvs_settings& st
 {
     const HostView& rv = c->views[ref];
     std::vector<Seed> out;
-    for (const HostFeature& f : c->feats) {
-        bool use = feature_has_view(f, ref);
-        for (size_t k = 0; !use && k < gsel.size(); ++k) if (feature_has_view(f, gsel[k])) use = true;
-        if (!use) continue;
+    // "use feature if visible in reference view or at least one neighboring view" (dmrecon.cc:260-276), in feature order
+    std::vector<int> ids;
+    if (ref < (int)c->view_feats.size()) ids = c->view_feats[ref];
+    for (int g : gsel) if (g >= 0 && g < (int)c->view_feats.size()) ids.insert(ids.end(), c->view_feats[g].begin(), c->view_feats[g].end());
+    std::sort(ids.begin(), ids.end());
+    ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
+    for (int fi : ids) {
+        const HostFeature& f = c->feats[fi];
         if (!point_in_frustum(rv, f.pos)) continue;
         if (!in_aabb(f.pos, st)) continue;
         float cp[3], sp[3];
@@ -387,7 +393,10 @@ __global__ void k_export_rgb(const uchar4* __restrict__ src, int w, int h, int p
 // ------------------------------------------------------------------------------------------------
 // kernels: patch optimisation + frontier
 // ------------------------------------------------------------------------------------------------
-constexpr int OPT_WARPS = 4;
+#ifndef OPT_WARPS_PER_BLOCK
+#define OPT_WARPS_PER_BLOCK 4
+#endif
+constexpr int OPT_WARPS = OPT_WARPS_PER_BLOCK;
 #ifndef OPT_MIN_BLOCKS
 #define OPT_MIN_BLOCKS 5     // registers per thread <= 65536 / (OPT_MIN_BLOCKS * 128) -> 96; tuned on B200, profiles/r1_notes.md
 #endif
@@ -741,6 +750,14 @@ int b200mvs_create(int device, int n_views, b200mvs_ctx** out)
     b200mvs_ctx* ctx = nullptr;
     if (!out || n_views <= 0) return fail(nullptr, B200MVS_ERR_INVALID_ARG, "b200mvs_create: bad arguments");
     *out = nullptr;
+    if (device == B200MVS_DEVICE_NONE) {
+        // planning context: cameras, features, global view selection (pure host logic); every compute entry point fails
+        ctx = new b200mvs_ctx();
+        ctx->device = B200MVS_DEVICE_NONE;
+        ctx->views.resize(n_views);
+        *out = ctx;
+        return 0;
+    }
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)
@@ -775,6 +792,7 @@ int b200mvs_create(int device, int n_views, b200mvs_ctx** out)
 void b200mvs_destroy(b200mvs_ctx* ctx)
 {
     if (!ctx) return;
+    if (ctx->device == B200MVS_DEVICE_NONE) { delete ctx; return; }
     cudaSetDevice(ctx->device);
     for (HostView& v : ctx->views) if (v.d_base) cudaFree(v.d_base);
     if (ctx->d_views) cudaFree(ctx->d_views);
@@ -792,6 +810,7 @@ int b200mvs_upload_view(b200mvs_ctx* ctx, int id, const uint8_t* rgb, int w, int
 {
     if (!ctx) return B200MVS_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> lk(ctx->mtx);
+    if (ctx->device == B200MVS_DEVICE_NONE) return fail(ctx, B200MVS_ERR_CUDA, "planning context (B200MVS_DEVICE_NONE): no CUDA device, b200mvs has no CPU fallback");
     if (id < 0 || id >= (int)ctx->views.size() || !rgb || w < 2 || h < 2 || !ppoint || !rot || !trans)
         return fail(ctx, B200MVS_ERR_INVALID_ARG, "b200mvs_upload_view: bad arguments");
     if (channels < 1 || channels > 4) return fail(ctx, B200MVS_ERR_INVALID_ARG, "Image with invalid number of channels");
@@ -814,6 +833,7 @@ int b200mvs_upload_view_device(b200mvs_ctx* ctx, int id, const uint8_t* rgb_dev,
 {
     if (!ctx) return B200MVS_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> lk(ctx->mtx);
+    if (ctx->device == B200MVS_DEVICE_NONE) return fail(ctx, B200MVS_ERR_CUDA, "planning context (B200MVS_DEVICE_NONE): no CUDA device, b200mvs has no CPU fallback");
     if (id < 0 || id >= (int)ctx->views.size() || !rgb_dev || w < 2 || h < 2 || !ppoint || !rot || !trans)
         return fail(ctx, B200MVS_ERR_INVALID_ARG, "b200mvs_upload_view_device: bad arguments");
     CK(cudaSetDevice(ctx->device));
@@ -831,7 +851,7 @@ int b200mvs_set_view_camera(b200mvs_ctx* ctx, int id, int w, int h, float flen, 
     std::lock_guard<std::mutex> lk(ctx->mtx);
     if (id < 0 || id >= (int)ctx->views.size() || w < 2 || h < 2 || !ppoint || !rot || !trans)
         return fail(ctx, B200MVS_ERR_INVALID_ARG, "b200mvs_set_view_camera: bad arguments");
-    CK(cudaSetDevice(ctx->device));
+    if (ctx->device != B200MVS_DEVICE_NONE) CK(cudaSetDevice(ctx->device));
     return upload_common(ctx, id, nullptr, w, h, 3, flen, paspect, ppoint, rot, trans, ctx->stream);
 }
 
@@ -845,6 +865,14 @@ int b200mvs_set_features(b200mvs_ctx* ctx, int n, const float* pos, const int32_
         std::memcpy(ctx->feats[i].pos, pos + 3 * i, 12);
         ctx->feats[i].refs.assign(ids + off[i], ids + off[i + 1]);
     }
+    // Feature3D::contains_view_id (bundle.cc:15-21) for every view at once
+    ctx->view_feats.assign(ctx->views.size(), std::vector<int>());
+    for (int i = 0; i < n; ++i)
+        for (int vid : ctx->feats[i].refs)
+            if (vid >= 0 && vid < (int)ctx->views.size()) {
+                std::vector<int>& vf = ctx->view_feats[vid];
+                if (vf.empty() || vf.back() != i) vf.push_back(i);
+            }
     return 0;
 }
 
@@ -866,6 +894,7 @@ int b200mvs_get_level(b200mvs_ctx* ctx, int id, int level, int* w, int* h, uint8
     if (h) *h = L.h;
     if (!rgb) return 0;
     if (!v.has_image) return fail(ctx, B200MVS_ERR_INVALID_ARG, "color image of view %d is not loaded", id);
+    if (ctx->device == B200MVS_DEVICE_NONE) return fail(ctx, B200MVS_ERR_CUDA, "planning context: no CUDA device");
     CK(cudaSetDevice(ctx->device));
     uint8_t* d = nullptr;
     CK(cudaMalloc(&d, (size_t)L.w * L.h * 3));
@@ -896,6 +925,7 @@ int b200mvs_optimize_patches(b200mvs_ctx* ctx, const b200mvs_settings* s, int re
 {
     if (!ctx) return B200MVS_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> lk(ctx->mtx);
+    if (ctx->device == B200MVS_DEVICE_NONE) return fail(ctx, B200MVS_ERR_CUDA, "planning context (B200MVS_DEVICE_NONE): no CUDA device, b200mvs has no CPU fallback");
     int rc = check_settings(ctx, s);
     if (rc) return rc;
     if (ref < 0 || ref >= (int)ctx->views.size()) return fail(ctx, B200MVS_ERR_INVALID_ARG, "Master view index out of bounds");
@@ -975,6 +1005,7 @@ int b200mvs_reconstruct(b200mvs_ctx* ctx, const b200mvs_settings* s, int n_refs,
 {
     if (!ctx) return B200MVS_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> lk(ctx->mtx);
+    if (ctx->device == B200MVS_DEVICE_NONE) return fail(ctx, B200MVS_ERR_CUDA, "planning context (B200MVS_DEVICE_NONE): no CUDA device, b200mvs has no CPU fallback");
     int rc = check_settings(ctx, s);
     if (rc) return rc;
     if (n_refs < 1 || !refs || n_refs > 4000) return fail(ctx, B200MVS_ERR_INVALID_ARG, "b200mvs_reconstruct: bad arguments");
