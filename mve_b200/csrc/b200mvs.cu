@@ -151,21 +151,6 @@ bool point_in_frustum(const HostView& v, const float* wp)
 }
 inline float foot_print(const HostView& v, int level, const float* p) { float c[3]; world_to_cam(v, p, c); return c[2] * v.lv[level].invproj[0]; }
 
-// mvs_tools.h:46-53
-float parallax(const float* p, const HostView& a, const HostView& b)
-{
-    float d1[3] = {p[0] - a.campos[0], p[1] - a.campos[1], p[2] - a.campos[2]};
-    float d2[3] = {p[0] - b.campos[0], p[1] - b.campos[1], p[2] - b.campos[2]};
-    normalize3(d1); normalize3(d2);
-    const float dp = std::max(std::min(dot3(d1, d2), 1.f), -1.f);
-    return std::acos(dp) * 180.f / 3.141592653589793f;
-}
-
-bool feature_has_view(const HostFeature& f, int id)
-{
-    for (int r : f.refs) if (r == id) return true;
-    return false;
-}
 bool in_aabb(const float* p, const b200mvs_settings& s)
 {
     for (int i = 0; i < 3; ++i) if (p[i] < s.aabb_min[i] || p[i] > s.aabb_max[i]) return false;
@@ -406,9 +391,9 @@ constexpr int OPT_WARPS = OPT_WARPS_PER_BLOCK;
 // hit rate made it 14 % slower - profiles/r1_notes.md.)
 constexpr int OPT_ENTRIES_PER_BLOCK = OPT_WARPS;
 __global__ void __launch_bounds__(OPT_WARPS * 32, OPT_MIN_BLOCKS)
-k_optimize(const Entry* __restrict__ in, PatchOut* __restrict__ out, const unsigned long long* __restrict__ n_ptr, int n_max,
+k_optimize(const Entry* __restrict__ in, PatchOut* __restrict__ out, const unsigned long long* n_ptr, int n_max,
            const DevSettings* __restrict__ st, const JobParams* __restrict__ jobs, const ViewParams* __restrict__ views,
-           const float* __restrict__ g_lut, unsigned long long* __restrict__ counters)
+           const float* __restrict__ g_lut, unsigned long long* counters)
 {
     __shared__ float lut[256];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = g_lut[i];
@@ -452,7 +437,7 @@ __global__ void k_select(Entry* __restrict__ cur, int n, const JobParams* __rest
 // Round step C (second half): the winning bid of each pixel runs, the others are carried to the next round.
 __global__ void k_pick(const Entry* __restrict__ cur, int n, const JobParams* __restrict__ jobs,
                        Entry* __restrict__ run, Entry* __restrict__ next, unsigned long long cap,
-                       unsigned long long* __restrict__ counters)
+                       unsigned long long* counters)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -471,9 +456,9 @@ __global__ void k_pick(const Entry* __restrict__ cur, int n, const JobParams* __
 }
 
 // Round step D: commit (dmrecon.cc:377-398).  One winner per pixel, so plain stores.
-__global__ void k_commit(const Entry* __restrict__ run, const PatchOut* __restrict__ res, const unsigned long long* __restrict__ n_ptr,
+__global__ void k_commit(const Entry* __restrict__ run, const PatchOut* __restrict__ res, const unsigned long long* n_ptr,
                          const JobParams* __restrict__ jobs, unsigned char* __restrict__ written,
-                         unsigned long long* __restrict__ counters, unsigned long long* __restrict__ filled)
+                         unsigned long long* counters, unsigned long long* filled)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (int)*n_ptr) return;
@@ -500,8 +485,8 @@ __global__ void k_commit(const Entry* __restrict__ run, const PatchOut* __restri
 
 // Round step E: push the 4-neighbours of every committed pixel (dmrecon.cc:400-431).
 __global__ void k_expand(const Entry* __restrict__ run, const PatchOut* __restrict__ res, const unsigned char* __restrict__ written,
-                         const unsigned long long* __restrict__ n_ptr, const JobParams* __restrict__ jobs,
-                         Entry* __restrict__ next, unsigned long long cap, unsigned long long* __restrict__ counters)
+                         const unsigned long long* n_ptr, const JobParams* __restrict__ jobs,
+                         Entry* __restrict__ next, unsigned long long cap, unsigned long long* counters)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (int)*n_ptr) return;
@@ -529,7 +514,7 @@ __global__ void k_expand(const Entry* __restrict__ run, const PatchOut* __restri
 
 // Seeds (dmrecon.cc:296-326): per pixel the most confident seed, first in feature order on ties.
 __global__ void k_seed_select(const Entry* __restrict__ seeds, const PatchOut* __restrict__ res, int n,
-                              const JobParams* __restrict__ jobs, unsigned long long* __restrict__ counters)
+                              const JobParams* __restrict__ jobs, unsigned long long* counters)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -543,7 +528,7 @@ __global__ void k_seed_select(const Entry* __restrict__ seeds, const PatchOut* _
 }
 __global__ void k_seed_commit(const Entry* __restrict__ seeds, const PatchOut* __restrict__ res, int n,
                               const JobParams* __restrict__ jobs, Entry* __restrict__ next, unsigned long long cap,
-                              unsigned long long* __restrict__ counters, unsigned long long* __restrict__ filled)
+                              unsigned long long* counters, unsigned long long* filled)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;

@@ -178,3 +178,38 @@ def test_config_C1_full_size_vs_oracle():
     # with the reference default of 4 local neighbours a 4-view scene cannot reconstruct anything
     maps4, st4 = g.reconstruct(dmrecon.Settings(scale=s.scale), [0])
     assert int(st4.n_filled) == 0
+
+
+@pytest.mark.parametrize("name,view,kw", [
+    ("T0", 2, dict(use_color_scale=0)),                       # --nocolorscale (patch_optimization.cc:83-84)
+    ("T0", 2, dict(global_vs_max=6)),                         # -n 6: fewer global candidates
+    ("T0", 4, dict(max_iterations=9)),                        # fewer Gauss-Newton iterations: more unconverged patches
+    ("T0", 1, dict(min_ncc=0.5, accept_ncc=0.75)),            # stricter thresholds: more view replacement / failures
+    ("T1", 3, dict(scale=2)),                                 # a coarser reference level than the fixture's
+    ("T2", 5, dict(nr_recon_neighbors=3)),                    # --local-neighbors=3 on the orbit scene
+])
+def test_settings_variants_vs_oracle(ctx, name, view, kw):
+    """Non-default mvs::Settings: patch-level parity on the whole execution trace + maps under the same schedule."""
+    from mve_b200 import dmrecon
+    from oracle import oracle_py as O
+    s, g, o = ctx(name)
+    base = dict(scale=s.scale, nr_recon_neighbors=s.nr_recon_neighbors)
+    base.update(kw)
+    gs, os_ = dmrecon.Settings(**base), O.default_settings(**base)
+    assert g.global_view_selection(gs, view) == o.global_view_selection(os_, view)
+    r = o.reconstruct(os_, view, trace_cap=100000)
+    got = g.optimize_patches(gs, view, o.global_view_selection(os_, view), r["trace_in"])
+    c = patch_compare(got, r["trace_out"])
+    n = c["n"]
+    assert c["ok_mismatch"] <= max(2, 0.003 * n) and c["ids_mismatch"] <= max(2, 0.003 * n), (c["ok_mismatch"], c["ids_mismatch"], n)
+    if c["both"].sum() > 100:
+        assert np.percentile(c["rel"], 99) < 5e-5
+        assert np.percentile(c["conf_abs"], 99) < 2e-4
+    maps, st = g.reconstruct(gs, [view])
+    rw = o.reconstruct_wavefront(os_, view, 0.0)
+    iou, rel, both = map_stats(rw["depth"], maps[0]["depth"])
+    if (rw["depth"] > 0).sum() > 500:
+        assert iou > (0.95 if name == "T2" else 0.99), iou
+        assert np.percentile(rel, 99) < (2e-2 if name == "T2" else 3e-3)
+    else:
+        assert (maps[0]["depth"] > 0).sum() <= 600
