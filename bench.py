@@ -371,6 +371,13 @@ def _main(real_stdout):
                 "kernel_share_of_device_time": ms_kernel / max(1e-9, sum(s.ms_total_device for s in stats)),
                 "impl_sample_sets": sum(int(s.n_sample_sets) for s in stats), "impl_opts": sum(int(s.n_opt) for s in stats),
                 "impl_bytes_300_per_set_GBs": (300.0 * sum(int(s.n_sample_sets) for s in stats) / (ms_kernel * 1e-3) / 1e9) if ms_kernel > 0 else None}
+    # context only: the same launches against the fp32 SIMT peak with SURVEY.md 8(d)'s ~110 kFLOP per reference
+    # PatchOptimization (oracle count per filled pixel x filled pixels)
+    opf = float(consts.get("opt_per_filled_px", 0.0))
+    if ms_kernel > 0 and opf > 0:
+        tf = 110e3 * opf * filled_local / (ms_kernel * 1e-3) / 1e12
+        roofline["fp32_context"] = {"achieved_tflops": tf, "peak_tflops": 74.0, "frac": tf / 74.0,
+                                    "note": "148 SM x 128 lanes x 2 x 1.965 GHz (derived, not measured); 110 kFLOP per reference optimisation"}
 
     # ---- cpu_baseline (rank 0, N = 1 only): the reference's own CPU dmrecon on this box's host cores ----
     cpu_baseline = None
