@@ -203,6 +203,8 @@ std::vector<int> global_view_selection(const b200mvs_ctx* c, const b200mvs_setti
         std::vector<float> base;         // parallax-with-ref and resolution terms (:78-87)
         std::vector<unsigned char> taken_ref;   // whether the ref-parallax branch multiplied (keeps `score = 1 * q*q` order)
         std::vector<std::vector<std::pair<int, float>>> extra;   // factors != 1 of selected views, ascending view id
+        float benefit = 0.f;             // benefitFromView of the last evaluation
+        bool dirty = true;
     };
     std::vector<Cand> cand(nv);
     std::vector<char> avail(nv, 1);
@@ -230,10 +232,13 @@ std::vector<int> global_view_selection(const b200mvs_ctx* c, const b200mvs_setti
             C.base[k] = score;
         }
     }
-    // SingleView::seesFeature (single_view.h:166-174) as a dense table; direction of a selected view per feature id
+    // per feature: the (candidate, position in its feature list) entries that hold it - SingleView::seesFeature
+    // (single_view.h:166-174) turned around
+    std::vector<std::vector<std::pair<int, int>>> entries_of(nf);
+    for (int i = 0; i < nv; ++i)
+        if (avail[i])
+            for (size_t k = 0; k < featInd[i].size(); ++k) entries_of[featInd[i][k]].push_back(std::make_pair(i, (int)k));
     std::vector<int> selected;
-    std::vector<std::vector<float>> sel_dir(nv);     // [view][3 * feature id], filled when the view gets selected
-    std::vector<std::vector<bool>> sees(nv);
     bool found = true;
     while (found && selected.size() < st.global_vs_max) {
         float maxBenefit = 0.f;
@@ -241,38 +246,42 @@ std::vector<int> global_view_selection(const b200mvs_ctx* c, const b200mvs_setti
         found = false;
         for (int i = 0; i < nv; ++i) {
             if (!avail[i]) continue;
-            const Cand& C = cand[i];
-            float benefit = 0;
-            const size_t n = featInd[i].size();
-            for (size_t k = 0; k < n; ++k) {
-                float score = C.base[k];
-                for (const std::pair<int, float>& e : C.extra[k]) score *= e.second;
-                benefit += score;
+            Cand& C = cand[i];
+            if (C.dirty) {
+                // recomputed only when a factor of this candidate changed since the last round: the same operations on
+                // the same operands give the same float, so caching cannot change the result
+                float benefit = 0;
+                const size_t n = featInd[i].size();
+                for (size_t k = 0; k < n; ++k) {
+                    float score = C.base[k];
+                    for (const std::pair<int, float>& e : C.extra[k]) score *= e.second;
+                    benefit += score;
+                }
+                C.benefit = benefit;
+                C.dirty = false;
             }
-            if (benefit > maxBenefit) { maxBenefit = benefit; maxView = i; found = true; }
+            if (C.benefit > maxBenefit) { maxBenefit = C.benefit; maxView = i; found = true; }
         }
         if (!found) break;
         selected.insert(std::upper_bound(selected.begin(), selected.end(), maxView), maxView);
         avail[maxView] = 0;
-        // fold the new view's factors into every remaining candidate
+        // fold the new view's factors into every remaining candidate.  Only (candidate, feature) entries whose feature
+        // the new view sees can change (global_view_selection.cc:90-92), so walk the new view's features and, through the
+        // per-feature list of entries, the candidates that hold each of them.
         const int sv = maxView;
-        sees[sv].assign(nf, false);
-        sel_dir[sv].assign(3 * nf, 0.f);
-        for (size_t k = 0; k < featInd[sv].size(); ++k) {
-            const int fid = featInd[sv][k];
-            sees[sv][fid] = true;
-            std::memcpy(&sel_dir[sv][3 * (size_t)fid], &cand[sv].dir[3 * k], 12);
-        }
-        for (int i = 0; i < nv; ++i) {
-            if (!avail[i]) continue;
-            Cand& C = cand[i];
-            for (size_t k = 0; k < featInd[i].size(); ++k) {
-                const int fid = featInd[i][k];
-                if (!sees[sv][fid]) continue;
-                const float f = plx_factor(&sel_dir[sv][3 * (size_t)fid], &C.dir[3 * k]);
+        for (size_t ks = 0; ks < featInd[sv].size(); ++ks) {
+            const int fid = featInd[sv][ks];
+            if (ks > 0 && featInd[sv][ks - 1] == fid) continue;        // seesFeature() is a predicate: a duplicate adds nothing
+            const float* ds = &cand[sv].dir[3 * ks];
+            for (const std::pair<int, int>& ik : entries_of[fid]) {
+                const int i = ik.first, k = ik.second;
+                if (!avail[i]) continue;
+                Cand& C = cand[i];
+                const float f = plx_factor(ds, &C.dir[3 * k]);
                 if (f != 1.f) {
                     std::vector<std::pair<int, float>>& ex = C.extra[k];
                     ex.insert(std::upper_bound(ex.begin(), ex.end(), std::make_pair(sv, -1e30f)), std::make_pair(sv, f));
+                    C.dirty = true;
                 }
             }
         }
