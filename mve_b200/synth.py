@@ -76,6 +76,9 @@ CONFIGS: Dict[str, Dict] = {
                surface="bumps", features=600, scale=1),
     "T2": dict(seed=13, views=12, width=160, height=120, layout="orbit", surface="sphere",
                features=800, scale=0, orbit_views_per_ring=6),
+    # odd image dimensions at every pyramid level: exercises the principal-point correction of image_pyramid.cc:39-44
+    "T4": dict(seed=15, views=6, width=161, height=121, layout="grid", grid=(3, 2), pitch=0.8,
+               surface="bumps", features=300, scale=1),
     # many candidates: global view selection must pick 20 of 39 (images are tiny, they do not matter for it)
     "T3": dict(seed=14, views=40, width=96, height=72, layout="grid", grid=(10, 4), pitch=0.45,
                surface="bumps", features=1500, scale=0),

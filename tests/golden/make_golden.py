@@ -133,4 +133,5 @@ if __name__ == "__main__":
     mint("T0", [0, 3])
     mint("T1", [4])
     mint("T2", [0])
+    mint("T4", [1])
     mint_gvs_only("T3")

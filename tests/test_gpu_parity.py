@@ -40,7 +40,7 @@ def _settings(s, **kw):
             O.default_settings(scale=s.scale, nr_recon_neighbors=s.nr_recon_neighbors, **kw))
 
 
-@pytest.mark.parametrize("name", ["T0", "T1", "T2"])
+@pytest.mark.parametrize("name", ["T0", "T1", "T2", "T4"])
 def test_pyramid_bit_exact(ctx, name):
     s, g, o = ctx(name)
     for v in range(s.n_views):
@@ -49,9 +49,11 @@ def test_pyramid_bit_exact(ctx, name):
             assert (g.level(v, l) == o.level(v, l)).all(), (v, l)
     if name == "T1":
         assert (g.level(4, 1) == golden_ref("T1")["undist_4"]).all()     # bytes written by the reference
+    if name == "T4":
+        assert (g.level(1, 1) == golden_ref("T4")["undist_1"]).all()     # odd dimensions at every level
 
 
-@pytest.mark.parametrize("name", ["T0", "T1", "T2", "T3"])
+@pytest.mark.parametrize("name", ["T0", "T1", "T2", "T3", "T4"])
 def test_global_view_selection_exact(ctx, name):
     s, g, o = ctx(name)
     ref = golden_ref(name)
@@ -63,7 +65,7 @@ def test_global_view_selection_exact(ctx, name):
             assert o.global_view_selection(os_, v) == want
 
 
-@pytest.mark.parametrize("name", ["T0", "T1", "T2"])
+@pytest.mark.parametrize("name", ["T0", "T1", "T2", "T4"])
 def test_patches_vs_reference_golden(ctx, name):
     """mvs::PatchOptimization results of the compiled reference (ref_harness) on identical inputs."""
     s, g, o = ctx(name)
@@ -98,6 +100,7 @@ def test_patches_vs_oracle_trace(ctx, name, view):
 
 
 @pytest.mark.parametrize("name,view,tol", [("T0", 0, (0.995, 2e-3)), ("T0", 3, (0.995, 2e-3)), ("T1", 4, (0.995, 2e-3)),
+                                           ("T4", 1, (0.995, 2e-3)),
                                            ("T2", 0, (0.97, 1e-2))])
 def test_maps_vs_oracle_same_schedule(ctx, name, view, tol):
     """DMRecon::start on the GPU vs the restatement running the identical frontier schedule."""
@@ -115,7 +118,7 @@ def test_maps_vs_oracle_same_schedule(ctx, name, view, tol):
     assert int(st.n_seeds_processed) == int(r["stats"]["n_seeds_processed"])
 
 
-@pytest.mark.parametrize("name,view", [("T0", 0), ("T0", 3), ("T1", 4)])
+@pytest.mark.parametrize("name,view", [("T0", 0), ("T0", 3), ("T1", 4), ("T4", 1)])
 def test_maps_vs_reference_cli_golden(ctx, name, view):
     """depth-L<s>/conf-L<s>/dz-L<s> written by the unmodified apps/dmrecon CLI."""
     s, g, o = ctx(name)
@@ -213,3 +216,33 @@ def test_settings_variants_vs_oracle(ctx, name, view, kw):
         assert np.percentile(rel, 99) < (2e-2 if name == "T2" else 3e-3)
     else:
         assert (maps[0]["depth"] > 0).sum() <= 600
+
+
+def test_mixed_resolution_neighbours():
+    """Ragged inputs: two neighbour views are given at half resolution (their own pyramid level 1, same relative
+    intrinsics), so the mip-level choice (patch_sampler.cc:76-91) differs per view."""
+    from mve_b200 import dmrecon, synth
+    from oracle import oracle_py as O
+    base = golden_scene("T0")
+    o0 = O.OracleScene(base)
+    imgs = list(base.images)
+    for v in (1, 4):
+        imgs[v] = o0.level(v, 1)
+    s = synth.Scene(name="T0-mixed", width=base.width, height=base.height, images=imgs, flen=base.flen, paspect=base.paspect,
+                    ppoint=base.ppoint, rot=base.rot, trans=base.trans, feat_pos=base.feat_pos, feat_refs=base.feat_refs, scale=0)
+    g = dmrecon.Scene.from_synth(s)
+    o = O.OracleScene(s)
+    assert g.num_levels(1) == o.num_levels(1) == o0.num_levels(1) - 1
+    gs, os_ = dmrecon.Settings(), O.default_settings()
+    for view in (0, 1):
+        assert g.global_view_selection(gs, view) == o.global_view_selection(os_, view)
+        r = o.reconstruct(os_, view, trace_cap=100000)
+        got = g.optimize_patches(gs, view, o.global_view_selection(os_, view), r["trace_in"])
+        c = patch_compare(got, r["trace_out"])
+        assert c["ok_mismatch"] <= 0.003 * c["n"] and c["ids_mismatch"] <= 0.003 * c["n"]
+        assert np.percentile(c["rel"], 99) < 5e-5
+        maps, _ = g.reconstruct(gs, [view])
+        rw = o.reconstruct_wavefront(os_, view, 0.0)
+        iou, rel, both = map_stats(rw["depth"], maps[0]["depth"])
+        assert iou > 0.99 and np.percentile(rel, 99) < 3e-3
+        assert (maps[0]["depth"] > 0).mean() > 0.3

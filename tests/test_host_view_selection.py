@@ -17,7 +17,7 @@ def _planning_scene(s):
     return g
 
 
-@pytest.mark.parametrize("name", ["T0", "T1", "T2", "T3"])
+@pytest.mark.parametrize("name", ["T0", "T1", "T2", "T3", "T4"])
 def test_global_view_selection_matches_reference(name):
     from mve_b200 import dmrecon
     s = golden_scene(name)

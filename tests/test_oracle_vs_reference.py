@@ -45,9 +45,12 @@ def test_pyramid_bit_exact(osc):
     s, sc = osc("T1")
     ref = golden_ref("T1")
     assert (sc.level(4, s.scale) == ref["undist_4"]).all()
+    # odd dimensions (161x121 -> 81x61): clamped taps at the right / bottom edge
+    s, sc = osc("T4")
+    assert (sc.level(1, s.scale) == golden_ref("T4")["undist_1"]).all()
 
 
-@pytest.mark.parametrize("name", ["T0", "T1", "T2", "T3"])
+@pytest.mark.parametrize("name", ["T0", "T1", "T2", "T3", "T4"])
 def test_global_view_selection_exact(osc, name):
     """Integer result of GlobalViewSelection (global_view_selection.cc:34-101) for default and -n 3."""
     s, sc = osc(name)
@@ -58,7 +61,7 @@ def test_global_view_selection_exact(osc, name):
             assert sc.global_view_selection(st, v) == ref["%s_%d" % (tag, v)].tolist(), (name, tag, v)
 
 
-@pytest.mark.parametrize("name", ["T0", "T1", "T2"])
+@pytest.mark.parametrize("name", ["T0", "T1", "T2", "T4"])
 def test_patch_optimization_vs_reference(osc, name):
     """mvs::PatchOptimization through ref_harness: same inputs -> same view ids, floats within FP noise."""
     s, sc = osc(name)
@@ -80,11 +83,12 @@ def test_patch_optimization_vs_reference(osc, name):
 # amplifies FP noise through its thresholded decisions, so the reference's OWN maps move by this much when its
 # compiler flags change.  T0/T1 are the well-conditioned cases.
 MAP_TOL = {"T0": dict(iou=0.995, p99=2e-3, mx=2e-2, conf=5e-3, dz=5e-3),
+           "T4": dict(iou=0.995, p99=2e-3, mx=2e-2, conf=5e-3, dz=5e-3),   # odd sizes: principal point moves per level
            "T1": dict(iou=0.995, p99=2e-3, mx=2e-2, conf=5e-3, dz=5e-3),
            "T2": dict(iou=0.98, p99=1e-2, mx=5e-2, conf=1e-1, dz=1e-2)}
 
 
-@pytest.mark.parametrize("name,views", [("T0", [0, 3]), ("T1", [4]), ("T2", [0])])
+@pytest.mark.parametrize("name,views", [("T0", [0, 3]), ("T1", [4]), ("T2", [0]), ("T4", [1])])
 def test_maps_vs_reference_cli(osc, name, views):
     """Whole depth/conf/dz maps of the unmodified apps/dmrecon CLI vs the restatement in strict priority order."""
     s, sc = osc(name)
