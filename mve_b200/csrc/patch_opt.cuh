@@ -19,7 +19,11 @@
 //     sums of the 3x3 normal equations (patch_optimization.cc:326-343) are formed per lane in fp32
 //     (<= 12 products) and across the lanes in fp64, then solved in fp64 inside the pass.
 #pragma once
+#if defined(B200MVS_HOST_EMU)
+#include "simt_emu.h"      // tests/emu: runs this very file on the CPU, 32 host threads per warp (test infrastructure)
+#else
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 #include <cstddef>
 
@@ -100,8 +104,13 @@ __device__ __forceinline__ float warp_max(float v)
 // reference itself is built with -funsafe-math-optimizations (Makefile.inc:5), i.e. without IEEE guarantees for these
 // operations; the effect on parity is measured by tests/test_gpu_parity.py.  Everything that decides integers on the
 // host (global view selection, seeds, pyramid) stays IEEE.
+#if defined(B200MVS_HOST_EMU)
+__device__ __forceinline__ float rcp_fast(float x) { return 1.f / x; }
+__device__ __forceinline__ float rsqrt_fast(float x) { return 1.f / sqrtf(x); }
+#else
 __device__ __forceinline__ float rcp_fast(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float rsqrt_fast(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+#endif
 
 // Batched butterflies: reducing K values together halves the number of live values at each of the first log2(K)
 // steps, so 4 sums cost 10 shuffles instead of 20 (2 sums: 7 instead of 10).  Every lane receives all totals, and all
