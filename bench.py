@@ -351,10 +351,11 @@ def _main(real_stdout):
     ms_kernel = sum(s.ms_patch_kernel for s in stats)
     n_launch = sum(int(s.n_patch_launches) for s in stats)
     achieved = (bpp * filled_local / (ms_kernel * 1e-3)) / 1e9 if ms_kernel > 0 and bpp > 0 else None
-    traffic, traffic_src = None, None
+    traffic, traffic_src, ncu_context = None, None, None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "r1_kopt_final_traffic.json")))
         traffic = tj["dram_bytes_per_launch_mean"]
+        ncu_context = tj.get("ncu_context")
         traffic_src = "ncu --set full capture of %d mid-run launches (%.0f patches each): profiles/r1_kopt_final_traffic.json" % (
             len(tj["launches"]), tj["patches_per_launch_mean"])
     except Exception:
@@ -371,6 +372,8 @@ def _main(real_stdout):
                 "kernel_share_of_device_time": ms_kernel / max(1e-9, sum(s.ms_total_device for s in stats)),
                 "impl_sample_sets": sum(int(s.n_sample_sets) for s in stats), "impl_opts": sum(int(s.n_opt) for s in stats),
                 "impl_bytes_300_per_set_GBs": (300.0 * sum(int(s.n_sample_sets) for s in stats) / (ms_kernel * 1e-3) / 1e9) if ms_kernel > 0 else None}
+    if ncu_context:
+        roofline["ncu_context"] = ncu_context      # what actually bounds the kernel (issue slots / L1), from the committed capture
     # context only: the same launches against the fp32 SIMT peak with SURVEY.md 8(d)'s ~110 kFLOP per reference
     # PatchOptimization (oracle count per filled pixel x filled pixels)
     opf = float(consts.get("opt_per_filled_px", 0.0))
