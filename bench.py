@@ -210,6 +210,8 @@ def _main(real_stdout):
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     args = ap.parse_args()
+    args.steps = max(1, args.steps)
+    args.warmup = max(0, args.warmup)
     if args.impl == "reference":
         return reference_arm(args, real_stdout)
 
