@@ -51,8 +51,14 @@ typedef struct b200mvs_settings {
     int32_t  use_color_scale;     /* settings.h:40  = 1     */
     float    aabb_min[3];         /* settings.h:44          */
     float    aabb_max[3];         /* settings.h:45          */
-    /* engine knob (no reference counterpart): frontier confidence band, <= 0 disables */
+    /* Engine knobs (no reference counterpart; DESIGN.md "Frontier schedule").  The reference pops strictly by
+     * descending confidence (dmrecon.h:72-76); the GPU advances a whole frontier per round.  Both knobs restrict a
+     * round to the most confident queued entries of each view so that the order approaches the reference's:
+     *   frontier_band  > 0: only entries within this confidence distance of the view's most confident entry run;
+     *   frontier_topk  > 0: only about the K most confident entries of each view run (confidence resolution 1/8192).
+     * 0 / 0 (default): every queued entry runs each round (fastest). */
     float    frontier_band;
+    uint32_t frontier_topk;
 } b200mvs_settings;
 
 /* Fills the defaults of settings.h:22-52. */
@@ -62,7 +68,8 @@ void b200mvs_default_settings(b200mvs_settings* s);
  * (fancy_progress_printer.cc:84-91, apps/umve/viewinspect/imageoperations.cc:177-184). */
 typedef struct b200mvs_progress {
     volatile int32_t  status;     /* ReconStatus: 0 idle, 1 globalvs, 2 features, 3 queue, 4 saving, 5 cancelled */
-    volatile int32_t  cancelled;  /* set from outside to cancel; polled once per frontier round */
+    volatile int32_t  cancelled;  /* set from outside (any thread) to cancel; relayed to the running kernel within ~0.2 ms,
+                                     honoured at the next frontier round; any view's flag stops the whole batch */
     volatile uint64_t filled;
     volatile uint64_t queue_size;
     volatile uint64_t start_time;
@@ -111,10 +118,13 @@ typedef struct b200mvs_stats {
     uint64_t n_seeds_processed;   /* "Processed N features" (dmrecon.cc:286)                    */
     uint64_t n_seeds_success;     /* "... from which N succeeded optimization" (dmrecon.cc:301) */
     uint64_t n_entries_peak;      /* peak frontier size                                         */
-    double   ms_patch_kernel;     /* summed CUDA-event time of the patch optimisation kernel    */
+    double   ms_patch_kernel;     /* CUDA-event time of the kernel that runs the patch optimisations (reconstruct: the
+                                     persistent frontier kernel, seeds + all rounds in one launch) */
     double   ms_total_device;     /* CUDA-event time first launch -> last launch of the call    */
-    uint64_t n_patch_launches;    /* launches of the patch optimisation kernel                  */
+    uint64_t n_patch_launches;    /* launches of the kernel that runs the patch optimisations   */
     uint64_t n_kernel_launches;   /* all kernel launches of the call                            */
+    double   ms_optimise_phases;  /* part of ms_patch_kernel spent in the optimise phases (rest: queue bookkeeping + barriers) */
+    uint64_t n_grid_barriers;     /* grid-wide barriers executed by the persistent kernel       */
 } b200mvs_stats;
 
 /* ---- lifecycle (mvs::DMRecon ctor/dtor, dmrecon.cc:30-87; ImagePyramidCache, image_pyramid.cc:99-160) ---- */

@@ -8,6 +8,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <chrono>
 #include <ctime>
 #include <mutex>
 #include <string>
@@ -58,6 +59,31 @@ static_assert(sizeof(Entry) == 32, "Entry layout");
 
 enum Counter { C_RUN = 0, C_NEXT = 1, C_OVERFLOW = 2, C_SETS = 3, C_OPTS = 4, C_SEED_OK = 5, C_FILLED = 6, C_NUM = 8 };
 
+constexpr int HIST_FINE = 8192;                 // confidence bins of the eligibility threshold: bin = conf * 8192
+constexpr int HIST_COARSE = 64;                 // one coarse bin per 128 fine bins
+constexpr int HIST_PER_JOB = HIST_FINE + HIST_COARSE;
+constexpr int DEFER_BIT = 1 << 27;              // Entry::jobdir flag: below this round's threshold, carried unchanged
+enum Phase { PH_SEED = 0, PH_SELECT = 1, PH_THRESHOLD = 2, PH_PICK = 3, PH_OPT = 4, PH_COMMIT = 5, PH_EXPAND = 6, PH_NUM = 8 };
+enum Stop { ST_RUN = 0, ST_CANCELLED = 2, ST_OVERFLOW = 3 };
+
+struct FrontierCtl {                            // device memory, zeroed before the launch
+    unsigned long long bar;                     // grid barrier ticket counter
+    unsigned long long nlist[2];                // entries in list[0] / list[1]
+    unsigned long long nrun;                    // winners of the current round
+    unsigned long long ticket;                  // next patch of the current optimise phase
+    unsigned long long rounds, peak, run_total, barriers;
+    unsigned long long ns[PH_NUM];              // %globaltimer time per phase, measured by CTA 0
+    int stop;
+    int pad;
+};
+
+struct HostMirror {                             // mapped pinned host memory
+    volatile int cancel;                        // host -> device
+    volatile int pad;
+    volatile unsigned long long round, queue;   // device -> host
+    volatile unsigned long long filled[1];      // [n_jobs]
+};
+
 template <typename T> struct DevBuf {
     T* p = nullptr;
     size_t cap = 0;
@@ -94,7 +120,12 @@ struct b200mvs_ctx {
     DevBuf<JobParams> d_jobs;
     DevBuf<DevSettings> d_settings;
     DevBuf<unsigned char> maps;        // all per-job maps of the current batch
+    DevBuf<FrontierCtl> ctl;
+    DevBuf<unsigned> hist;
+    DevBuf<int> thr_bin;
+    int frontier_grid = 0;             // CTAs of the cooperative launch (= what fits on the chip)
     unsigned long long* h_counters = nullptr;   // pinned
+    unsigned long long* h_mirror = nullptr;     // pinned + mapped: HostMirror
     std::vector<cudaEvent_t> ev_pool;
 };
 
@@ -431,136 +462,358 @@ __device__ __forceinline__ unsigned long long entry_key(const Entry& e)
     return ((unsigned long long)__float_as_uint(e.conf) << 8) | (unsigned long long)(7 - ((e.jobdir >> 24) & 7));
 }
 
-// Round step A+C (first half): stale test (dmrecon.cc:371) and per-pixel bid.
-__global__ void k_select(Entry* __restrict__ cur, int n, const JobParams* __restrict__ jobs)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    Entry e = cur[i];
-    const JobParams& J = jobs[e.jobdir & 0xFFFFFF];
-    const int idx = ((e.xy >> 16) & 0xFFFF) * J.W + (e.xy & 0xFFFF);
-    if (J.conf[idx] > e.conf) { cur[i].jobdir = -1; return; }
-    atomicMax(&J.sel[idx], entry_key(e));
-}
+// ---- the whole region growing of a batch in ONE persistent kernel -------------------------------------------------------
+// processFeatures + processQueue (dmrecon.cc:244-434) as frontier rounds (DESIGN.md "Frontier schedule").  The grid is
+// launched cooperatively with exactly as many CTAs as fit on the chip; the phases of a round are separated by a grid-wide
+// barrier instead of kernel boundaries, the patch optimisations of a round are handed out warp by warp through a ticket
+// counter, and the host is not involved until the queue is empty: progress goes out and the cancel flag comes in through
+// mapped pinned memory once per round (Progress, progress.h:27-43; dmrecon.cc:353).
+struct FrontierParams {
+    Entry* list[2];
+    Entry* run;
+    PatchOut* res;
+    unsigned char* written;
+    unsigned long long cap;
+    int n_seeds, n_jobs;
+    const DevSettings* st;
+    const JobParams* jobs;
+    const ViewParams* views;
+    const float* lut;
+    unsigned long long* counters;               // Counter + filled per job
+    FrontierCtl* ctl;
+    unsigned* hist;                             // [n_jobs][HIST_PER_JOB], zero on entry (only with a threshold)
+    int* thr_bin;                               // [n_jobs]
+    HostMirror* host;
+    int band_bins;                              // frontier_band in fine bins (0 = off)
+    int topk;                                   // frontier_topk (0 = off)
+};
 
-// Round step C (second half): the winning bid of each pixel runs, the others are carried to the next round.
-__global__ void k_pick(const Entry* __restrict__ cur, int n, const JobParams* __restrict__ jobs,
-                       Entry* __restrict__ run, Entry* __restrict__ next, unsigned long long cap,
-                       unsigned long long* counters)
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const Entry e = cur[i];
-    if (e.jobdir == -1) return;
-    const JobParams& J = jobs[e.jobdir & 0xFFFFFF];
-    const int idx = ((e.xy >> 16) & 0xFFFF) * J.W + (e.xy & 0xFFFF);
-    const unsigned long long key = entry_key(e);
-    if (J.sel[idx] == key && atomicCAS(&J.sel[idx], key, 0ull) == key) {
-        const unsigned long long pos = atomicAdd(&counters[C_RUN], 1ull);
-        run[pos] = e;                       // |run| <= n <= capacity
-    } else {
-        const unsigned long long pos = atomicAdd(&counters[C_NEXT], 1ull);
-        if (pos < cap) next[pos] = e; else counters[C_OVERFLOW] = 1ull;
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// All CTAs are co-resident (cooperative launch), so a monotone ticket counter is a barrier: the k-th generation is
+// complete when the counter reaches k * gridDim.x.
+__device__ __forceinline__ void grid_barrier(unsigned long long* bar)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned long long nb = gridDim.x;
+        const unsigned long long t = atomicAdd(bar, 1ull);
+        const unsigned long long target = (t / nb + 1ull) * nb;
+        while (ld_acquire_u64(bar) < target) __nanosleep(64);
+        __threadfence();
     }
+    __syncthreads();
 }
-
-// Round step D: commit (dmrecon.cc:377-398).  One winner per pixel, so plain stores.
-__global__ void k_commit(const Entry* __restrict__ run, const PatchOut* __restrict__ res, const unsigned long long* n_ptr,
-                         const JobParams* __restrict__ jobs, unsigned char* __restrict__ written,
-                         unsigned long long* counters, unsigned long long* filled)
+__device__ __forceinline__ int conf_bin(float c)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (int)*n_ptr) return;
-    const Entry e = run[i];
-    const PatchOut r = res[i];
-    const int j = e.jobdir & 0xFFFFFF;
-    const JobParams& J = jobs[j];
-    const int idx = ((e.xy >> 16) & 0xFFFF) * J.W + (e.xy & 0xFFFF);
-    unsigned char w = 0;
-    if (!(r.conf == 0.f)) {
-        const float old = J.conf[idx];
-        if (old <= 0.f) atomicAdd(&filled[j], 1ull);
-        if (old < r.conf) {
-            J.depth[idx] = r.depth;
-            J.conf[idx] = r.conf;
-            J.dz[2 * idx] = r.dzI; J.dz[2 * idx + 1] = r.dzJ;
-            J.normal[3 * idx] = r.nx; J.normal[3 * idx + 1] = r.ny; J.normal[3 * idx + 2] = r.nz;
-            J.slots[idx] = r.slots;
-            w = 1;
-        }
-    }
-    written[i] = w;
+    const int b = (int)(c * (float)HIST_FINE);
+    return b < 0 ? 0 : (b > HIST_FINE - 1 ? HIST_FINE - 1 : b);
 }
-
-// Round step E: push the 4-neighbours of every committed pixel (dmrecon.cc:400-431).
-__global__ void k_expand(const Entry* __restrict__ run, const PatchOut* __restrict__ res, const unsigned char* __restrict__ written,
-                         const unsigned long long* n_ptr, const JobParams* __restrict__ jobs,
-                         Entry* __restrict__ next, unsigned long long cap, unsigned long long* counters)
+__device__ __forceinline__ Entry load_entry(const Entry* p)       // lists are rewritten by other SMs every round: bypass L1
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (int)*n_ptr) return;
-    if (!written[i]) return;
-    const Entry e = run[i];
-    const PatchOut r = res[i];
-    const int j = e.jobdir & 0xFFFFFF;
-    const JobParams& J = jobs[j];
-    const int x = e.xy & 0xFFFF, y = (e.xy >> 16) & 0xFFFF;
-    const int nx[4] = {x - 1, x + 1, x, x};
-    const int ny[4] = {y, y, y - 1, y + 1};
-#pragma unroll
-    for (int d = 0; d < 4; ++d) {
-        const float c = J.conf[ny[d] * J.W + nx[d]];
-        if (c < r.conf - 0.05f || c == 0.f) {
-            Entry o;
-            o.xy = nx[d] | (ny[d] << 16);
-            o.jobdir = j | (d << 24);
-            o.conf = r.conf; o.depth = r.depth; o.dzI = r.dzI; o.dzJ = r.dzJ; o.slots = r.slots; o.pad = 0;
-            const unsigned long long pos = atomicAdd(&counters[C_NEXT], 1ull);
-            if (pos < cap) next[pos] = o; else counters[C_OVERFLOW] = 1ull;
-        }
-    }
+    const int4 a = __ldcg(reinterpret_cast<const int4*>(p));
+    const int4 b = __ldcg(reinterpret_cast<const int4*>(p) + 1);
+    Entry e;
+    e.xy = a.x; e.jobdir = a.y; e.conf = __int_as_float(a.z); e.depth = __int_as_float(a.w);
+    e.dzI = __int_as_float(b.x); e.dzJ = __int_as_float(b.y); e.slots = (unsigned)b.z; e.pad = b.w;
+    return e;
 }
-
-// Seeds (dmrecon.cc:296-326): per pixel the most confident seed, first in feature order on ties.
-__global__ void k_seed_select(const Entry* __restrict__ seeds, const PatchOut* __restrict__ res, int n,
-                              const JobParams* __restrict__ jobs, unsigned long long* counters)
+__device__ __forceinline__ PatchOut load_result(const PatchOut* p)  // written by another SM in the optimise phase: bypass L1
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const PatchOut r = res[i];
-    if (!(r.conf > 0.f)) return;
-    atomicAdd(&counters[C_SEED_OK], 1ull);
-    const Entry e = seeds[i];
-    const JobParams& J = jobs[e.jobdir & 0xFFFFFF];
-    const int idx = ((e.xy >> 16) & 0xFFFF) * J.W + (e.xy & 0xFFFF);
-    atomicMax(&J.sel[idx], ((unsigned long long)__float_as_uint(r.conf) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i));
+    static_assert(sizeof(PatchOut) == 40, "PatchOut layout");
+    const int2* q = reinterpret_cast<const int2*>(p);
+    const int2 a = __ldcg(q), b = __ldcg(q + 1), c = __ldcg(q + 2), d = __ldcg(q + 3), e = __ldcg(q + 4);
+    PatchOut r;
+    r.conf = __int_as_float(a.x); r.depth = __int_as_float(a.y); r.dzI = __int_as_float(b.x); r.dzJ = __int_as_float(b.y);
+    r.nx = __int_as_float(c.x); r.ny = __int_as_float(c.y); r.nz = __int_as_float(d.x); r.slots = (unsigned)d.y;
+    r.iterations = e.x; r.flags = e.y;
+    return r;
 }
-__global__ void k_seed_commit(const Entry* __restrict__ seeds, const PatchOut* __restrict__ res, int n,
-                              const JobParams* __restrict__ jobs, Entry* __restrict__ next, unsigned long long cap,
-                              unsigned long long* counters, unsigned long long* filled)
+__device__ __forceinline__ void push_entry(const FrontierParams& P, int q, const Entry& o)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const PatchOut r = res[i];
-    if (!(r.conf > 0.f)) return;
-    const Entry e = seeds[i];
-    const int j = e.jobdir & 0xFFFFFF;
-    const JobParams& J = jobs[j];
-    const int idx = ((e.xy >> 16) & 0xFFFF) * J.W + (e.xy & 0xFFFF);
-    const unsigned long long key = ((unsigned long long)__float_as_uint(r.conf) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i);
-    if (J.sel[idx] != key) return;
-    J.sel[idx] = 0ull;
-    atomicAdd(&filled[j], 1ull);
+    const unsigned long long pos = atomicAdd(&P.ctl->nlist[q], 1ull);
+    if (pos < P.cap) P.list[q][pos] = o; else P.counters[C_OVERFLOW] = 1ull;
+}
+__device__ __forceinline__ void write_pixel(const JobParams& J, int idx, const PatchOut& r)
+{
     J.depth[idx] = r.depth;
     J.conf[idx] = r.conf;
     J.dz[2 * idx] = r.dzI; J.dz[2 * idx + 1] = r.dzJ;
     J.normal[3 * idx] = r.nx; J.normal[3 * idx + 1] = r.ny; J.normal[3 * idx + 2] = r.nz;
     J.slots[idx] = r.slots;
-    Entry o;
-    o.xy = e.xy; o.jobdir = j | (4 << 24);
-    o.conf = r.conf; o.depth = r.depth; o.dzI = r.dzI; o.dzJ = r.dzJ; o.slots = r.slots; o.pad = 0;
-    const unsigned long long pos = atomicAdd(&counters[C_NEXT], 1ull);
-    if (pos < cap) next[pos] = o; else counters[C_OVERFLOW] = 1ull;
+}
+
+// Warps take patches of run[0..n) through the ticket counter until none is left.
+__device__ __forceinline__ void optimise_phase(const FrontierParams& P, unsigned long long n, const float* lut, int lane)
+{
+    unsigned sets = 0u, opts = 0u;
+    for (;;) {
+        unsigned long long w = 0ull;
+        if (lane == 0) w = atomicAdd(&P.ctl->ticket, 1ull);
+        w = __shfl_sync(FULL, w, 0);
+        if (w >= n) break;
+        const Entry e = load_entry(&P.run[w]);
+        PatchIn pi;
+        pi.x = e.xy & 0xFFFF; pi.y = (e.xy >> 16) & 0xFFFF;
+        pi.depth = e.depth; pi.dzI = e.dzI; pi.dzJ = e.dzJ; pi.slots = e.slots;
+        PatchOut po;
+        sets += optimize_patch(P.st, &P.jobs[e.jobdir & 0xFFFFFF], P.views, lut, lane, pi, po);
+        ++opts;
+        if (lane == 0) P.res[w] = po;
+    }
+    if (lane == 0 && opts) {
+        atomicAdd(&P.counters[C_SETS], (unsigned long long)sets);
+        atomicAdd(&P.counters[C_OPTS], (unsigned long long)opts);
+    }
+}
+
+// Eligibility threshold of one job from its confidence histogram (one warp).  topk: the largest bin t such that at least
+// `topk` entries have bin >= t (0 when there are fewer); band: (highest non-empty bin) - band_bins.  Both: the larger.
+__device__ __forceinline__ int threshold_of(const unsigned* hist, int lane, int band_bins, int topk)
+{
+    const unsigned* coarse = hist + HIST_FINE;
+    int t_top = 0, t_band = 0;
+    // coarse scan, descending: lane l looks at coarse bins 63 - l and 31 - l
+    const unsigned c_hi = __ldcg(&coarse[63 - lane]), c_lo = __ldcg(&coarse[31 - lane]);
+    if (band_bins > 0) {
+        const unsigned m_hi = __ballot_sync(FULL, c_hi != 0u), m_lo = __ballot_sync(FULL, c_lo != 0u);
+        int cb = -1;
+        if (m_hi) cb = 63 - (__ffs(m_hi) - 1); else if (m_lo) cb = 31 - (__ffs(m_lo) - 1);
+        if (cb >= 0) {
+            int top = -1;
+            for (int q = 3; q >= 0 && top < 0; --q) {
+                const unsigned v = __ldcg(&hist[cb * 128 + q * 32 + (31 - lane)]);
+                const unsigned m = __ballot_sync(FULL, v != 0u);
+                if (m) top = cb * 128 + q * 32 + 31 - (__ffs(m) - 1);
+            }
+            t_band = top - band_bins;
+            if (t_band < 0) t_band = 0;
+        }
+    }
+    if (topk > 0) {
+        unsigned need = (unsigned)topk, before = 0u;
+        int cb = -1;
+        for (int half = 0; half < 2 && cb < 0; ++half) {
+            const unsigned c = half == 0 ? c_hi : c_lo;
+            unsigned incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
+            const unsigned m = __ballot_sync(FULL, before + incl >= need);
+            if (m) {
+                const int l = __ffs(m) - 1;
+                cb = (half == 0 ? 63 : 31) - l;
+                before += __shfl_sync(FULL, incl, l) - __shfl_sync(FULL, c, l);
+            } else
+                before += __shfl_sync(FULL, incl, 31);
+        }
+        if (cb >= 0) {
+            for (int q = 3; q >= 0; --q) {
+                const unsigned c = __ldcg(&hist[cb * 128 + q * 32 + (31 - lane)]);
+                unsigned incl = c;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
+                const unsigned m = __ballot_sync(FULL, before + incl >= need);
+                if (m) { t_top = cb * 128 + q * 32 + 31 - (__ffs(m) - 1); break; }
+                before += __shfl_sync(FULL, incl, 31);
+            }
+        }
+    }
+    return t_top > t_band ? t_top : t_band;
+}
+
+__global__ void __launch_bounds__(OPT_WARPS * 32, OPT_MIN_BLOCKS)
+k_frontier(const FrontierParams P)
+{
+    __shared__ float lut[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = P.lut[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, gthreads = (size_t)gridDim.x * blockDim.x;
+    FrontierCtl* const ctl = P.ctl;
+    unsigned long long* const cnt = P.counters;
+    unsigned long long* const filled = cnt + C_NUM;
+    const bool lead = blockIdx.x == 0 && threadIdx.x == 0;
+    const bool thresholded = P.band_bins > 0 || P.topk > 0;
+    unsigned long long t_prev = lead ? global_timer_ns() : 0ull;
+    unsigned long long n_bar = 0ull;
+#define PHASE_END(ph) do { grid_barrier(&ctl->bar); ++n_bar; if (lead) { const unsigned long long t_ = global_timer_ns(); ctl->ns[ph] += t_ - t_prev; t_prev = t_; } } while (0)
+
+    // ---- processQueue as frontier rounds (dmrecon.cc:334-434) ----
+    // Round 0 optimises the seeds (processFeatures, dmrecon.cc:293-326: per pixel the most confident seed is committed, first
+    // in feature order on ties), every later round one frontier.  The optimise phase has ONE call site so that the patch
+    // optimisation code exists once in the instruction stream.
+    int p = 1;                                                   // the seed round pushes into list[0]
+    bool seed_round = P.n_seeds > 0;
+    for (;;) {
+        unsigned long long n_cur = seed_round ? (unsigned long long)P.n_seeds : __ldcg(&ctl->nlist[p]);
+        if (n_cur > P.cap) n_cur = P.cap;
+        if (__ldcg(&ctl->stop) != ST_RUN || n_cur == 0ull) break;
+        unsigned long long n_run = n_cur;
+        if (!seed_round) {
+        Entry* const cur = P.list[p];
+        if (blockIdx.x == 0) {                                  // progress out (dmrecon.cc:355-364)
+            if (threadIdx.x == 0) { P.host->round = ctl->rounds; P.host->queue = n_cur; }
+            for (int j = threadIdx.x; j < P.n_jobs; j += blockDim.x) P.host->filled[j] = __ldcg(&filled[j]);
+        }
+        // A: stale test (dmrecon.cc:371-373); without a threshold the per-pixel bid follows immediately
+        for (size_t i = gtid; i < n_cur; i += gthreads) {
+            const Entry e = load_entry(&cur[i]);
+            const int j = e.jobdir & 0xFFFFFF;
+            const JobParams& J = P.jobs[j];
+            const int idx = ((e.xy >> 16) & 0xFFFF) * J.W + (e.xy & 0xFFFF);
+            if (__ldcg(&J.conf[idx]) > e.conf) { cur[i].jobdir = -1; continue; }
+            if (!thresholded) atomicMax(&J.sel[idx], entry_key(e));
+            else {
+                const int b = conf_bin(e.conf);
+                atomicAdd(&P.hist[(size_t)j * HIST_PER_JOB + b], 1u);
+                atomicAdd(&P.hist[(size_t)j * HIST_PER_JOB + HIST_FINE + (b >> 7)], 1u);
+            }
+        }
+        PHASE_END(PH_SELECT);
+        if (thresholded) {
+            // B: this round's eligibility threshold of every job, then the bids of the eligible entries
+            for (int j = blockIdx.x * OPT_WARPS + (threadIdx.x >> 5); j < P.n_jobs; j += gridDim.x * OPT_WARPS) {
+                const int t = threshold_of(P.hist + (size_t)j * HIST_PER_JOB, lane, P.band_bins, P.topk);
+                if (lane == 0) P.thr_bin[j] = t;
+            }
+            PHASE_END(PH_THRESHOLD);
+            for (size_t i = gtid; i < n_cur; i += gthreads) {
+                const Entry e = load_entry(&cur[i]);
+                if (e.jobdir == -1) continue;
+                const int j = e.jobdir & 0xFFFFFF;
+                if (conf_bin(e.conf) < __ldcg(&P.thr_bin[j])) { cur[i].jobdir = e.jobdir | DEFER_BIT; continue; }
+                const JobParams& J = P.jobs[j];
+                const int idx = ((e.xy >> 16) & 0xFFFF) * J.W + (e.xy & 0xFFFF);
+                atomicMax(&J.sel[idx], entry_key(e));
+            }
+            PHASE_END(PH_THRESHOLD);
+        }
+        // C: the winning bid of each pixel runs, every other live entry is carried to the next round (the reference would
+        // pop it later and apply the stale test then)
+        for (size_t i = gtid; i < n_cur; i += gthreads) {
+            Entry e = load_entry(&cur[i]);
+            if (e.jobdir == -1) continue;
+            if (e.jobdir & DEFER_BIT) { e.jobdir &= ~DEFER_BIT; push_entry(P, 1 - p, e); continue; }
+            const JobParams& J = P.jobs[e.jobdir & 0xFFFFFF];
+            const int idx = ((e.xy >> 16) & 0xFFFF) * J.W + (e.xy & 0xFFFF);
+            const unsigned long long key = entry_key(e);
+            if (__ldcg(&J.sel[idx]) == key && atomicCAS(&J.sel[idx], key, 0ull) == key) {
+                const unsigned long long pos = atomicAdd(&ctl->nrun, 1ull);
+                P.run[pos] = e;                                   // |run| <= n_cur <= capacity
+            } else
+                push_entry(P, 1 - p, e);
+        }
+        if (thresholded)
+            for (size_t i = gtid; i < (size_t)P.n_jobs * HIST_PER_JOB; i += gthreads) P.hist[i] = 0u;
+        PHASE_END(PH_PICK);
+        n_run = __ldcg(&ctl->nrun);
+        if (lead) ctl->nlist[p] = 0ull;                           // consumed; the round after the next pushes into it
+        }
+        // the PatchOptimizations of the round
+        optimise_phase(P, n_run, lut, lane);
+        if (seed_round) {
+            PHASE_END(PH_SEED);
+            for (size_t i = gtid; i < (size_t)P.n_seeds; i += gthreads) {
+                const float c = __ldcg(&P.res[i].conf);
+                if (!(c > 0.f)) continue;
+                atomicAdd(&cnt[C_SEED_OK], 1ull);
+                const Entry e = load_entry(&P.run[i]);
+                const JobParams& J = P.jobs[e.jobdir & 0xFFFFFF];
+                const int idx = ((e.xy >> 16) & 0xFFFF) * J.W + (e.xy & 0xFFFF);
+                atomicMax(&J.sel[idx], ((unsigned long long)__float_as_uint(c) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i));
+            }
+            PHASE_END(PH_SELECT);
+            for (size_t i = gtid; i < (size_t)P.n_seeds; i += gthreads) {
+                const float c = __ldcg(&P.res[i].conf);
+                if (!(c > 0.f)) continue;
+                const Entry e = load_entry(&P.run[i]);
+                const int j = e.jobdir & 0xFFFFFF;
+                const JobParams& J = P.jobs[j];
+                const int idx = ((e.xy >> 16) & 0xFFFF) * J.W + (e.xy & 0xFFFF);
+                const unsigned long long key = ((unsigned long long)__float_as_uint(c) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i);
+                if (__ldcg(&J.sel[idx]) != key) continue;
+                J.sel[idx] = 0ull;
+                atomicAdd(&filled[j], 1ull);
+                const PatchOut r = load_result(&P.res[i]);
+                write_pixel(J, idx, r);
+                Entry o;
+                o.xy = e.xy; o.jobdir = j | (4 << 24);
+                o.conf = r.conf; o.depth = r.depth; o.dzI = r.dzI; o.dzJ = r.dzJ; o.slots = r.slots; o.pad = 0;
+                push_entry(P, 0, o);
+            }
+            if (lead) ctl->ticket = 0ull;
+            PHASE_END(PH_COMMIT);
+            seed_round = false;
+            p = 0;
+            continue;
+        }
+        PHASE_END(PH_OPT);
+        // D: commit (dmrecon.cc:377-398).  One winner per pixel, so plain stores.
+        for (size_t i = gtid; i < n_run; i += gthreads) {
+            const Entry e = load_entry(&P.run[i]);
+            const PatchOut r = load_result(&P.res[i]);
+            const int j = e.jobdir & 0xFFFFFF;
+            const JobParams& J = P.jobs[j];
+            const int idx = ((e.xy >> 16) & 0xFFFF) * J.W + (e.xy & 0xFFFF);
+            unsigned char w = 0;
+            if (!(r.conf == 0.f)) {
+                const float old = __ldcg(&J.conf[idx]);
+                if (old <= 0.f) atomicAdd(&filled[j], 1ull);
+                if (old < r.conf) { write_pixel(J, idx, r); w = 1; }
+            }
+            P.written[i] = w;
+        }
+        if (lead) { ctl->nrun = 0ull; ctl->ticket = 0ull; }
+        PHASE_END(PH_COMMIT);
+        // E: after ALL commits, push the 4-neighbours of every committed pixel (dmrecon.cc:400-431)
+        for (size_t i = gtid; i < n_run; i += gthreads) {
+            if (!P.written[i]) continue;
+            const Entry e = load_entry(&P.run[i]);
+            const PatchOut r = load_result(&P.res[i]);
+            const int j = e.jobdir & 0xFFFFFF;
+            const JobParams& J = P.jobs[j];
+            const int x = e.xy & 0xFFFF, y = (e.xy >> 16) & 0xFFFF;
+            const int nx[4] = {x - 1, x + 1, x, x};
+            const int ny[4] = {y, y, y - 1, y + 1};
+#pragma unroll
+            for (int d = 0; d < 4; ++d) {
+                const float c = __ldcg(&J.conf[ny[d] * J.W + nx[d]]);
+                if (c < r.conf - 0.05f || c == 0.f) {
+                    Entry o;
+                    o.xy = nx[d] | (ny[d] << 16);
+                    o.jobdir = j | (d << 24);
+                    o.conf = r.conf; o.depth = r.depth; o.dzI = r.dzI; o.dzJ = r.dzJ; o.slots = r.slots; o.pad = 0;
+                    push_entry(P, 1 - p, o);
+                }
+            }
+        }
+        if (lead) {
+            ctl->rounds += 1ull;
+            ctl->run_total += n_run;
+            if (n_cur > ctl->peak) ctl->peak = n_cur;
+            if (P.host->cancel) ctl->stop = ST_CANCELLED;
+            else if (__ldcg(&cnt[C_OVERFLOW])) ctl->stop = ST_OVERFLOW;
+        }
+        PHASE_END(PH_EXPAND);
+        p ^= 1;
+    }
+    if (lead) ctl->barriers = n_bar;
+    if (blockIdx.x == 0) {
+        if (threadIdx.x == 0) { P.host->round = ctl->rounds; P.host->queue = 0ull; }
+        for (int j = threadIdx.x; j < P.n_jobs; j += blockDim.x) P.host->filled[j] = __ldcg(&filled[j]);
+    }
+#undef PHASE_END
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -576,8 +829,8 @@ int check_settings(b200mvs_ctx* ctx, const b200mvs_settings* s)
         return fail(ctx, B200MVS_ERR_UNSUPPORTED, "nrReconNeighbors must be in 1..%d", B200MVS_MAX_LOCAL_VIEWS);
     if (s->global_vs_max < 1 || s->global_vs_max > B200MVS_MAX_GLOBAL_VIEWS)
         return fail(ctx, B200MVS_ERR_UNSUPPORTED, "globalVSMax must be in 1..%d", B200MVS_MAX_GLOBAL_VIEWS);
-    if (s->frontier_band > 0.f)
-        return fail(ctx, B200MVS_ERR_UNSUPPORTED, "frontier_band > 0 is reserved");
+    if (!(s->frontier_band >= 0.f) || s->frontier_band > 1.f)
+        return fail(ctx, B200MVS_ERR_INVALID_ARG, "frontier_band must be in [0, 1]");
     return 0;
 }
 
@@ -734,7 +987,7 @@ void b200mvs_default_settings(b200mvs_settings* s)
     s->filter_width = 5; s->min_ncc = 0.3f; s->min_parallax = 10.0f; s->accept_ncc = 0.6f; s->min_refine_diff = 0.001f;
     s->max_iterations = 20; s->nr_recon_neighbors = 4; s->global_vs_max = 20; s->scale = 0; s->use_color_scale = 1;
     for (int i = 0; i < 3; ++i) { s->aabb_min[i] = -3.402823466e+38f; s->aabb_max[i] = 3.402823466e+38f; }
-    s->frontier_band = 0.f;
+    s->frontier_band = 0.f; s->frontier_topk = 0;
 }
 
 const char* b200mvs_last_error(const b200mvs_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
@@ -771,6 +1024,7 @@ int b200mvs_create(int device, int n_views, b200mvs_ctx** out)
     if ((e = cudaMalloc(&ctx->d_views, sizeof(ViewParams) * n_views)) != cudaSuccess) return bail("cudaMalloc(views)", e);
     if ((e = cudaMalloc(&ctx->d_lut, 256 * sizeof(float))) != cudaSuccess) return bail("cudaMalloc(lut)", e);
     if ((e = cudaMallocHost(&ctx->h_counters, sizeof(unsigned long long) * 4096)) != cudaSuccess) return bail("cudaMallocHost", e);
+    if ((e = cudaHostAlloc(&ctx->h_mirror, sizeof(unsigned long long) * 4200, cudaHostAllocMapped)) != cudaSuccess) return bail("cudaHostAlloc", e);
     // sRGB code value -> linear: the formula documented at mvs_tools.cc:21-29; tests/test_lut.py checks the
     // 256 floats against the reference table.
     float lut[256];
@@ -792,8 +1046,10 @@ void b200mvs_destroy(b200mvs_ctx* ctx)
     if (ctx->d_views) cudaFree(ctx->d_views);
     if (ctx->d_lut) cudaFree(ctx->d_lut);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+    if (ctx->h_mirror) cudaFreeHost(ctx->h_mirror);
     ctx->ent_a.release(); ctx->ent_b.release(); ctx->run_in.release(); ctx->run_out.release(); ctx->written.release();
     ctx->counters.release(); ctx->d_jobs.release(); ctx->d_settings.release(); ctx->maps.release();
+    ctx->ctl.release(); ctx->hist.release(); ctx->thr_bin.release();
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -1096,7 +1352,10 @@ int b200mvs_reconstruct(b200mvs_ctx* ctx, const b200mvs_settings* s, int n_refs,
         CK(cudaMemsetAsync(base, 0, total_px * (per_px - 4), st));               // sel, depth, conf, dz, normal = 0
         CK(cudaMemsetAsync(slots, 0xFF, total_px * 4, st));
     }
-    const size_t cap = std::max<size_t>(std::max<size_t>(total_px, seeds.size()), 1u << 16);
+    // Frontier capacity: a round holds at most one running entry per pixel plus the carried losers; 2 entries per pixel
+    // was never approached (peak on the BASELINE scenes: 0.2 per pixel).  Exceeding it fails the call (ERR_OVERFLOW).
+    const size_t cap = std::max<size_t>(std::max<size_t>(2 * total_px, seeds.size()), 1u << 16);
+    const bool thresholded = s->frontier_band > 0.f || s->frontier_topk > 0;
     CK(ctx->ent_a.reserve(cap));
     CK(ctx->ent_b.reserve(cap));
     CK(ctx->run_in.reserve(cap));
@@ -1105,80 +1364,78 @@ int b200mvs_reconstruct(b200mvs_ctx* ctx, const b200mvs_settings* s, int n_refs,
     CK(ctx->counters.reserve(C_NUM + n_refs));
     CK(ctx->d_jobs.reserve(n_refs));
     CK(ctx->d_settings.reserve(1));
+    CK(ctx->ctl.reserve(1));
+    CK(ctx->thr_bin.reserve(n_refs));
+    if (thresholded) CK(ctx->hist.reserve((size_t)n_refs * HIST_PER_JOB));
     if ((size_t)(C_NUM + n_refs) > 4096) return fail(ctx, B200MVS_ERR_INVALID_ARG, "too many reference views in one batch");
     const DevSettings ds = to_dev(*s);
     CK(cudaMemcpyAsync(ctx->d_jobs.p, jobs.data(), sizeof(JobParams) * n_refs, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(ctx->d_settings.p, &ds, sizeof(ds), cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(ctx->counters.p, 0, sizeof(unsigned long long) * (C_NUM + n_refs), st));
-    unsigned long long* d_cnt = ctx->counters.p;
-    unsigned long long* d_filled = d_cnt + C_NUM;
+    CK(cudaMemsetAsync(ctx->ctl.p, 0, sizeof(FrontierCtl), st));
+    if (thresholded) CK(cudaMemsetAsync(ctx->hist.p, 0, sizeof(unsigned) * (size_t)n_refs * HIST_PER_JOB, st));
+    if (!seeds.empty()) CK(cudaMemcpyAsync(ctx->run_in.p, seeds.data(), sizeof(Entry) * seeds.size(), cudaMemcpyHostToDevice, st));
+    HostMirror* mirror = reinterpret_cast<HostMirror*>(ctx->h_mirror);
+    std::memset(ctx->h_mirror, 0, sizeof(HostMirror) + sizeof(unsigned long long) * n_refs);
 
-    size_t n_ev = 0;
-    std::vector<std::pair<size_t, size_t>> opt_events;
-    uint64_t launches = 0, opt_launches = 0;
-    cudaEvent_t ev_begin = get_event(ctx, n_ev++);
-    CK(cudaEventRecord(ev_begin, st));
+    FrontierParams P;
+    P.list[0] = ctx->ent_a.p; P.list[1] = ctx->ent_b.p;
+    P.run = ctx->run_in.p; P.res = ctx->run_out.p; P.written = ctx->written.p;
+    P.cap = cap; P.n_seeds = (int)seeds.size(); P.n_jobs = n_refs;
+    P.st = ctx->d_settings.p; P.jobs = ctx->d_jobs.p; P.views = ctx->d_views; P.lut = ctx->d_lut;
+    P.counters = ctx->counters.p; P.ctl = ctx->ctl.p; P.hist = ctx->hist.p; P.thr_bin = ctx->thr_bin.p;
+    P.host = mirror;
+    P.band_bins = s->frontier_band > 0.f ? std::max(1, (int)(s->frontier_band * (float)HIST_FINE)) : 0;
+    P.topk = (int)std::min<uint32_t>(s->frontier_topk, 1u << 30);
 
-    Entry* cur = ctx->ent_a.p;
-    Entry* nxt = ctx->ent_b.p;
-    size_t n_cur = 0;
-    // ---- seeds: processFeatures (dmrecon.cc:293-326) ----
-    if (!seeds.empty()) {
-        const int ns = (int)seeds.size();
-        CK(cudaMemcpyAsync(ctx->run_in.p, seeds.data(), sizeof(Entry) * ns, cudaMemcpyHostToDevice, st));
-        cudaEvent_t a = get_event(ctx, n_ev), b = get_event(ctx, n_ev + 1);
-        opt_events.push_back({n_ev, n_ev + 1}); n_ev += 2;
-        CK(cudaEventRecord(a, st));
-        k_optimize<<<(ns + OPT_ENTRIES_PER_BLOCK - 1) / OPT_ENTRIES_PER_BLOCK, OPT_WARPS * 32, 0, st>>>(ctx->run_in.p, ctx->run_out.p, nullptr, ns, ctx->d_settings.p,
-                                                                              ctx->d_jobs.p, ctx->d_views, ctx->d_lut, d_cnt);
-        CK(cudaEventRecord(b, st));
-        k_seed_select<<<(ns + 255) / 256, 256, 0, st>>>(ctx->run_in.p, ctx->run_out.p, ns, ctx->d_jobs.p, d_cnt);
-        k_seed_commit<<<(ns + 255) / 256, 256, 0, st>>>(ctx->run_in.p, ctx->run_out.p, ns, ctx->d_jobs.p, cur, cap, d_cnt, d_filled);
-        CK(cudaGetLastError());
-        launches += 3; opt_launches += 1;
-        CK(cudaMemcpyAsync(ctx->h_counters, d_cnt, sizeof(unsigned long long) * (C_NUM + n_refs), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        n_cur = (size_t)ctx->h_counters[C_NEXT];
-        if (stats) stats->n_seeds_success = ctx->h_counters[C_SEED_OK];
+    if (progress)                      // `if (progress.cancelled) return` at the head of every stage (dmrecon.cc:100-104,336)
+        for (int j = 0; j < n_refs; ++j)
+            if (progress[j].cancelled) {
+                for (int k = 0; k < n_refs; ++k) progress[k].status = 5;
+                return fail(ctx, B200MVS_ERR_CANCELLED, "reconstruction cancelled");
+            }
+    // ---- one cooperative launch: seeds + all frontier rounds (DESIGN.md "Frontier schedule") ----
+    if (ctx->frontier_grid == 0) {
+        int per_sm = 0, sms = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_frontier, OPT_WARPS * 32, 0));
+        CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+        if (per_sm < 1) return fail(ctx, B200MVS_ERR_CUDA, "k_frontier does not fit on an SM");
+        ctx->frontier_grid = per_sm * sms;
     }
-    // ---- processQueue as frontier rounds (dmrecon.cc:334-434; DESIGN.md "Frontier schedule") ----
-    uint64_t rounds = 0, peak = n_cur;
-    bool cancelled = false;
-    while (n_cur > 0) {
-        if (ctx->h_counters[C_OVERFLOW]) return fail(ctx, B200MVS_ERR_OVERFLOW, "frontier buffer overflow (capacity %zu entries)", cap);
-        if (progress) {
+    cudaEvent_t ev_begin = get_event(ctx, 0), ev_end = get_event(ctx, 1);
+    CK(cudaEventRecord(ev_begin, st));
+    {
+        void* args[] = {(void*)&P};
+        CK(cudaLaunchCooperativeKernel((const void*)k_frontier, dim3(ctx->frontier_grid), dim3(OPT_WARPS * 32), args, 0, st));
+    }
+    CK(cudaEventRecord(ev_end, st));
+    CK(cudaMemcpyAsync(ctx->h_counters, ctx->counters.p, sizeof(unsigned long long) * (C_NUM + n_refs), cudaMemcpyDeviceToHost, st));
+    FrontierCtl* h_ctl = reinterpret_cast<FrontierCtl*>(ctx->h_counters + 2048);
+    CK(cudaMemcpyAsync(h_ctl, ctx->ctl.p, sizeof(FrontierCtl), cudaMemcpyDeviceToHost, st));
+    cudaEvent_t ev_copied = get_event(ctx, 2);
+    CK(cudaEventRecord(ev_copied, st));
+    // While the kernel runs the host only relays: progress out (Progress::filled / queueSize, fancy_progress_printer.cc:84-91)
+    // and a cancel request in (imageoperations.cc:177-184) - any view's flag stops the batch at the next round.
+    if (progress) {
+        for (;;) {
+            const cudaError_t q = cudaEventQuery(ev_copied);
+            if (q == cudaSuccess) break;
+            if (q != cudaErrorNotReady) return fail(ctx, B200MVS_ERR_CUDA, "frontier kernel: %s", cudaGetErrorString(q));
+            const unsigned long long qs = mirror->queue;
             for (int j = 0; j < n_refs; ++j) {
                 progress[j].status = 3;
-                progress[j].filled = ctx->h_counters[C_NUM + j];
-                progress[j].queue_size = n_cur;
-                if (progress[j].cancelled) cancelled = true;
+                progress[j].filled = mirror->filled[j];
+                progress[j].queue_size = qs;
+                if (progress[j].cancelled) mirror->cancel = 1;
             }
-            if (cancelled) break;
+            std::this_thread::sleep_for(std::chrono::microseconds(200));
         }
-        ++rounds;
-        peak = std::max<uint64_t>(peak, n_cur);
-        const int n = (int)n_cur;
-        CK(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long) * 2, st));   // C_RUN, C_NEXT
-        k_select<<<(n + 255) / 256, 256, 0, st>>>(cur, n, ctx->d_jobs.p);
-        k_pick<<<(n + 255) / 256, 256, 0, st>>>(cur, n, ctx->d_jobs.p, ctx->run_in.p, nxt, cap, d_cnt);
-        cudaEvent_t a = get_event(ctx, n_ev), b = get_event(ctx, n_ev + 1);
-        opt_events.push_back({n_ev, n_ev + 1}); n_ev += 2;
-        CK(cudaEventRecord(a, st));
-        k_optimize<<<(n + OPT_ENTRIES_PER_BLOCK - 1) / OPT_ENTRIES_PER_BLOCK, OPT_WARPS * 32, 0, st>>>(ctx->run_in.p, ctx->run_out.p, d_cnt + C_RUN, n, ctx->d_settings.p,
-                                                                             ctx->d_jobs.p, ctx->d_views, ctx->d_lut, d_cnt);
-        CK(cudaEventRecord(b, st));
-        k_commit<<<(n + 255) / 256, 256, 0, st>>>(ctx->run_in.p, ctx->run_out.p, d_cnt + C_RUN, ctx->d_jobs.p, ctx->written.p, d_cnt, d_filled);
-        k_expand<<<(n + 255) / 256, 256, 0, st>>>(ctx->run_in.p, ctx->run_out.p, ctx->written.p, d_cnt + C_RUN, ctx->d_jobs.p, nxt, cap, d_cnt);
-        CK(cudaGetLastError());
-        launches += 5; opt_launches += 1;
-        CK(cudaMemcpyAsync(ctx->h_counters, d_cnt, sizeof(unsigned long long) * (C_NUM + n_refs), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        n_cur = (size_t)std::min<unsigned long long>(ctx->h_counters[C_NEXT], cap);
-        std::swap(cur, nxt);
     }
-    if (ctx->h_counters[C_OVERFLOW]) return fail(ctx, B200MVS_ERR_OVERFLOW, "frontier buffer overflow (capacity %zu entries)", cap);
-    cudaEvent_t ev_end = get_event(ctx, n_ev++);
-    CK(cudaEventRecord(ev_end, st));
+    CK(cudaStreamSynchronize(st));
+    const bool cancelled = h_ctl->stop == ST_CANCELLED;
+    if (ctx->h_counters[C_OVERFLOW] || h_ctl->stop == ST_OVERFLOW)
+        return fail(ctx, B200MVS_ERR_OVERFLOW, "frontier buffer overflow (capacity %zu entries)", cap);
+    if (stats) stats->n_seeds_success = ctx->h_counters[C_SEED_OK];
 
     // ---- results ----
     if (maps && !cancelled) {
@@ -1213,17 +1470,21 @@ int b200mvs_reconstruct(b200mvs_ctx* ctx, const b200mvs_settings* s, int n_refs,
     if (stats) {
         stats->n_opt = ctx->h_counters[C_OPTS];
         stats->n_sample_sets = ctx->h_counters[C_SETS];
-        stats->n_rounds = rounds;
+        stats->n_rounds = h_ctl->rounds;
         stats->n_filled = filled;
-        stats->n_entries_peak = peak;
-        stats->n_patch_launches = opt_launches;
-        stats->n_kernel_launches = launches;
-        double ms_opt = 0.0;
-        for (auto& pr : opt_events) { float ms = 0.f; cudaEventElapsedTime(&ms, ctx->ev_pool[pr.first], ctx->ev_pool[pr.second]); ms_opt += ms; }
+        stats->n_entries_peak = h_ctl->peak;
+        stats->n_patch_launches = 1;
+        stats->n_kernel_launches = 1;
         float ms_all = 0.f;
         cudaEventElapsedTime(&ms_all, ev_begin, ev_end);
-        stats->ms_patch_kernel = ms_opt;
+        // the optimise phases inside the persistent kernel, by %globaltimer of CTA 0 between the grid barriers
+        double ns_all = 0.0;
+        for (int k = 0; k < PH_NUM; ++k) ns_all += (double)h_ctl->ns[k];
+        const double ns_opt = (double)h_ctl->ns[PH_OPT] + (double)h_ctl->ns[PH_SEED];
+        stats->ms_patch_kernel = ms_all;
         stats->ms_total_device = ms_all;
+        stats->ms_optimise_phases = ns_all > 0.0 ? ms_all * ns_opt / ns_all : 0.0;
+        stats->n_grid_barriers = h_ctl->barriers;
     }
     if (cancelled) return fail(ctx, B200MVS_ERR_CANCELLED, "reconstruction cancelled");
     return 0;

@@ -35,7 +35,7 @@ class Settings(C.Structure):
                 ("accept_ncc", C.c_float), ("min_refine_diff", C.c_float), ("max_iterations", C.c_uint32),
                 ("nr_recon_neighbors", C.c_uint32), ("global_vs_max", C.c_uint32), ("scale", C.c_int32),
                 ("use_color_scale", C.c_int32), ("aabb_min", C.c_float * 3), ("aabb_max", C.c_float * 3),
-                ("frontier_band", C.c_float)]
+                ("frontier_band", C.c_float), ("frontier_topk", C.c_uint32)]
 
     def __init__(self, **kw):
         super().__init__()
@@ -61,7 +61,8 @@ class Stats(C.Structure):
     _fields_ = [("n_opt", C.c_uint64), ("n_sample_sets", C.c_uint64), ("n_rounds", C.c_uint64),
                 ("n_filled", C.c_uint64), ("n_seeds_processed", C.c_uint64), ("n_seeds_success", C.c_uint64),
                 ("n_entries_peak", C.c_uint64), ("ms_patch_kernel", C.c_double), ("ms_total_device", C.c_double),
-                ("n_patch_launches", C.c_uint64), ("n_kernel_launches", C.c_uint64)]
+                ("n_patch_launches", C.c_uint64), ("n_kernel_launches", C.c_uint64),
+                ("ms_optimise_phases", C.c_double), ("n_grid_barriers", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -215,9 +216,10 @@ class Scene:
         return out
 
     def reconstruct(self, settings: Settings, ref_views: Sequence[int], download: bool = True,
-                    want=("depth", "conf", "dz", "normal", "view_ids"), out=None):
+                    want=("depth", "conf", "dz", "normal", "view_ids"), out=None, progress=None):
         """DMRecon::start for a batch of reference views. Returns (list of map dicts or None, Stats).
-        out: optional list (one dict per view) of preallocated host arrays (e.g. pinned) to receive the maps."""
+        out: optional list (one dict per view) of preallocated host arrays (e.g. pinned) to receive the maps.
+        progress: optional (Progress * n) array, updated live; setting .cancelled from another thread cancels the run."""
         refs = np.asarray(ref_views, np.int32)
         n = len(refs)
         stats = Stats()
@@ -255,7 +257,7 @@ class Scene:
                 results.append(d)
                 for k in ("depth", "conf", "dz", "normal", "view_ids"):
                     setattr(maps_arr[j], k, d[k].ctypes.data if k in d else None)
-        rc = self._lib.b200mvs_reconstruct(self._h, C.byref(settings), n, _p(refs), maps_arr, None, C.byref(stats),
+        rc = self._lib.b200mvs_reconstruct(self._h, C.byref(settings), n, _p(refs), maps_arr, progress, C.byref(stats),
                                            C.byref(failed))
         if rc != 0:
             msg = self._lib.b200mvs_last_error(self._h).decode()

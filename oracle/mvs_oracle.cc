@@ -1075,7 +1075,10 @@ int mvs_oracle_reconstruct(mvs_oracle_scene* s, const mvs_oracle_settings* st, i
  * queue entry (the maps are only read by the stale test and the commit, dmrecon.cc:371,388-431), so
  * the entries of one round may be evaluated in any order / in parallel:
  *   round: A drop entries with conf[pixel] > entry.conf (stale test, dmrecon.cc:371)
- *          B entries with conf < max_conf_in_round - band are deferred to the next round (band <= 0: none)
+ *          B eligibility threshold of the round from the confidences of the non-stale entries, in bins of 1/8192
+ *            (bin = min(8191, (int)(conf * 8192))): band > 0: bin >= bin(max) - max(1, (int)(band * 8192));
+ *            topk > 0: bin >= the largest t with at least topk entries in bins >= t (0 if there are fewer);
+ *            both: the larger threshold; neither: every entry is eligible.  Entries below are deferred unchanged.
  *          C per pixel the eligible entry with the largest (conf, then smallest direction code) runs,
  *            the others are carried over to the next round
  *          D results with conf != 0 are committed when conf[pixel] < result.conf (dmrecon.cc:377-398)
@@ -1083,7 +1086,7 @@ int mvs_oracle_reconstruct(mvs_oracle_scene* s, const mvs_oracle_settings* st, i
  *            reference rule conf[nb] < conf - 0.05 || conf[nb] == 0 (dmrecon.cc:400-431)
  * Seeds: all features are optimised, per pixel the most confident (first in feature order on ties)
  * is committed and becomes a round-0 entry (equivalent to dmrecon.cc:296-326 followed by the stale test). */
-int mvs_oracle_reconstruct_wavefront(mvs_oracle_scene* s, const mvs_oracle_settings* st, int ref, float band,
+int mvs_oracle_reconstruct_wavefront(mvs_oracle_scene* s, const mvs_oracle_settings* st, int ref, float band, int topk,
                                      float* depth, float* conf, float* dz, float* normal, int32_t* view_ids,
                                      mvs_oracle_stats* stats)
 {
@@ -1160,6 +1163,8 @@ int mvs_oracle_reconstruct_wavefront(mvs_oracle_scene* s, const mvs_oracle_setti
     std::vector<int> winner(npix, -1);
     std::vector<mvs_oracle_patch_out> results;
     std::vector<int> run_list;
+    auto conf_bin = [](float c) { int b = (int)(c * 8192.0f); return b < 0 ? 0 : (b > 8191 ? 8191 : b); };
+    std::vector<unsigned> hist(8192);
     while (!cur.empty()) {
         S.n_spec_rounds++;
         next.clear();
@@ -1171,13 +1176,24 @@ int mvs_oracle_reconstruct_wavefront(mvs_oracle_scene* s, const mvs_oracle_setti
             if (conf[index] > e.conf) { e.dir = -1; S.n_stale++; continue; }
             maxc = std::max(maxc, e.conf);
         }
-        const float thr = band > 0.f ? maxc - band : -1e30f;
+        int thr_bin = 0;
+        if (band > 0.f || topk > 0) {
+            std::fill(hist.begin(), hist.end(), 0u);
+            int top = -1;
+            for (const WEntry& e : cur) if (e.dir >= 0) { const int b = conf_bin(e.conf); hist[b]++; top = std::max(top, b); }
+            if (band > 0.f && top >= 0) thr_bin = std::max(0, top - std::max(1, (int)(band * 8192.0f)));
+            if (topk > 0) {
+                unsigned long cum = 0; int t = 0;
+                for (int b = 8191; b >= 0; --b) { cum += hist[b]; if (cum >= (unsigned long)topk) { t = b; break; } }
+                thr_bin = std::max(thr_bin, t);
+            }
+        }
         /* C: per-pixel winner */
         run_list.clear();
         for (size_t i = 0; i < cur.size(); ++i) {
             WEntry& e = cur[i];
             if (e.dir < 0) continue;
-            if (e.conf < thr) { next.push_back(e); e.dir = -1; S.n_pops--; continue; }
+            if (conf_bin(e.conf) < thr_bin) { next.push_back(e); e.dir = -1; S.n_pops--; continue; }
             const int index = e.y * W + e.x;
             int& w = winner[index];
             if (w < 0) { w = (int)i; continue; }

@@ -118,8 +118,9 @@ int mvs_oracle_reconstruct(mvs_oracle_scene*, const mvs_oracle_settings*, int re
                            int64_t trace_cap, int64_t* trace_n, double max_seconds);
 
 /* Same reconstruction under the deterministic frontier schedule the GPU uses (see the comment at the
- * definition).  band <= 0: every queued entry runs each round. stats.n_spec_rounds = number of rounds. */
-int mvs_oracle_reconstruct_wavefront(mvs_oracle_scene*, const mvs_oracle_settings*, int ref_view, float band,
+ * definition).  band <= 0 and topk <= 0: every queued entry runs each round; otherwise only the entries at or above the round's
+ * confidence threshold (frontier_band / frontier_topk of include/b200mvs.h). stats.n_spec_rounds = number of rounds. */
+int mvs_oracle_reconstruct_wavefront(mvs_oracle_scene*, const mvs_oracle_settings*, int ref_view, float band, int topk,
                                      float* depth, float* conf, float* dz, float* normal, int32_t* view_ids,
                                      mvs_oracle_stats* stats);
 

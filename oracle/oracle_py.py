@@ -66,7 +66,7 @@ def _lib():
                                                 C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     lib.mvs_oracle_reconstruct.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 8 + \
                                           [C.c_int64, C.c_void_p, C.c_double]
-    lib.mvs_oracle_reconstruct_wavefront.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float] + [C.c_void_p] * 6
+    lib.mvs_oracle_reconstruct_wavefront.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int] + [C.c_void_p] * 6
     return lib
 
 
@@ -162,7 +162,7 @@ class OracleScene:
             res["trace_in"], res["trace_out"] = tin[:n], tout[:n]
         return res
 
-    def reconstruct_wavefront(self, st: Settings, ref: int, band: float = 0.0):
+    def reconstruct_wavefront(self, st: Settings, ref: int, band: float = 0.0, topk: int = 0):
         w, h = C.c_int(), C.c_int()
         self.lib.mvs_oracle_get_level(self.h, ref, st.scale, C.byref(w), C.byref(h), None)
         W, H = w.value, h.value
@@ -172,7 +172,7 @@ class OracleScene:
         normal = np.zeros((H, W, 3), np.float32)
         vids = np.zeros((H, W, 4), np.int32)
         stats = np.zeros(1, STATS)
-        rc = self.lib.mvs_oracle_reconstruct_wavefront(self.h, C.byref(st), ref, band, _p(depth), _p(conf), _p(dz),
+        rc = self.lib.mvs_oracle_reconstruct_wavefront(self.h, C.byref(st), ref, band, int(topk), _p(depth), _p(conf), _p(dz),
                                                        _p(normal), _p(vids), _p(stats))
         if rc != 0:
             raise RuntimeError("mvs_oracle_reconstruct_wavefront rc=%d" % rc)

@@ -118,6 +118,28 @@ def test_maps_vs_oracle_same_schedule(ctx, name, view, tol):
     assert int(st.n_seeds_processed) == int(r["stats"]["n_seeds_processed"])
 
 
+@pytest.mark.parametrize("name,view,band,topk", [("T0", 0, 0.003, 0), ("T0", 3, 0.0, 16), ("T1", 4, 0.0, 64), ("T1", 4, 0.01, 256)])
+def test_maps_vs_oracle_same_schedule_thresholded(ctx, name, view, band, topk):
+    """frontier_band / frontier_topk: the per-round confidence threshold (bins of 1/8192) is the same rule in the
+    restatement, so the maps must agree like under the plain frontier schedule; and the order moves towards the
+    reference's strict one (more rounds, closer to the strict maps)."""
+    from mve_b200 import dmrecon
+    s, g, o = ctx(name)
+    gs, os_ = _settings(s)
+    gs2 = dmrecon.Settings(scale=s.scale, nr_recon_neighbors=s.nr_recon_neighbors, frontier_band=band, frontier_topk=topk)
+    maps, st = g.reconstruct(gs2, [view])
+    m = maps[0]
+    r = o.reconstruct_wavefront(os_, view, band, topk)
+    iou, rel, both = map_stats(r["depth"], m["depth"])
+    assert iou > 0.995, iou
+    assert np.percentile(rel, 50) < 1e-5
+    assert np.percentile(rel, 99) < 2e-3
+    assert (m["view_ids"] == r["view_ids"]).all(-1)[both].mean() > 0.98
+    assert abs(int(st.n_rounds) - int(r["stats"]["n_spec_rounds"])) <= 0.05 * r["stats"]["n_spec_rounds"] + 2
+    plain, st0 = g.reconstruct(gs, [view])
+    assert int(st.n_rounds) > int(st0.n_rounds)
+
+
 @pytest.mark.parametrize("name,view", [("T0", 0), ("T0", 3), ("T1", 4), ("T4", 1)])
 def test_maps_vs_reference_cli_golden(ctx, name, view):
     """depth-L<s>/conf-L<s>/dz-L<s> written by the unmodified apps/dmrecon CLI."""

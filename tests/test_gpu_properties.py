@@ -195,6 +195,39 @@ def test_cancel():
     assert prog[0].status == 5
 
 
+def test_cancel_while_running():
+    """A cancel request raised from another thread while the persistent kernel runs (UMVE's cancel button,
+    apps/umve/viewinspect/imageoperations.cc:177-184) stops the batch at the next frontier round; live progress
+    (filled / queue_size, fancy_progress_printer.cc:84-91) is visible meanwhile."""
+    import threading
+    import time
+    from mve_b200 import dmrecon
+    s = golden_scene("T1")
+    g = dmrecon.Scene.from_synth(s)
+    st = dmrecon.Settings(scale=s.scale, frontier_topk=1)          # one pop per round and view: thousands of rounds
+    full, stats_full = g.reconstruct(st, [4])
+    prog = (dmrecon.Progress * 1)()
+    seen = []
+
+    def canceller():
+        t0 = time.time()
+        while time.time() - t0 < 20.0:
+            if prog[0].filled > 200:
+                seen.append((int(prog[0].filled), int(prog[0].queue_size), int(prog[0].status)))
+                prog[0].cancelled = 1
+                return
+            time.sleep(0.0005)
+    th = threading.Thread(target=canceller)
+    th.start()
+    with pytest.raises(dmrecon.B200MVSError) as e:
+        g.reconstruct(st, [4], progress=prog)
+    th.join()
+    assert e.value.code == -4
+    assert seen and seen[0][2] == 3 and seen[0][1] > 0
+    assert prog[0].status == 5
+    assert 200 < prog[0].filled < stats_full.n_filled
+
+
 def test_image_channel_variants():
     """Grey and RGBA inputs are expanded / stripped like image_pyramid.cc:65-73."""
     from mve_b200 import dmrecon
