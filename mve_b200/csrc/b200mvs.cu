@@ -29,6 +29,7 @@ struct HostLevel {
     int w = 0, h = 0, pitch = 0;
     float proj[9], invproj[9];
     uchar4* d_img = nullptr;
+    uint4* d_quad = nullptr;       // 2x2 neighbourhood of every texel, 16 bytes (patch_opt.cuh LevelParams::quad)
 };
 
 struct HostView {
@@ -39,7 +40,7 @@ struct HostView {
     float campos[3];
     float w2c[12];
     std::vector<HostLevel> lv;
-    uchar4* d_base = nullptr;      // one allocation for every level
+    uchar4* d_base = nullptr;      // one allocation for every level: the RGBX8 images, then their quad images
     size_t bytes = 0;
 };
 
@@ -57,7 +58,7 @@ struct Entry {                     // frontier queue entry = QueueData (dmrecon.
 };
 static_assert(sizeof(Entry) == 32, "Entry layout");
 
-enum Counter { C_RUN = 0, C_NEXT = 1, C_OVERFLOW = 2, C_SETS = 3, C_OPTS = 4, C_SEED_OK = 5, C_FILLED = 6, C_NUM = 8 };
+enum Counter { C_RUN = 0, C_NEXT = 1, C_OVERFLOW = 2, C_SETS = 3, C_OPTS = 4, C_SEED_OK = 5, C_FILLED = 6, C_TICKET = 7, C_NUM = 8 };
 
 constexpr int HIST_FINE = 8192;                 // confidence bins of the eligibility threshold: bin = conf * 8192
 constexpr int HIST_COARSE = 64;                 // one coarse bin per 128 fine bins
@@ -124,6 +125,7 @@ struct b200mvs_ctx {
     DevBuf<unsigned> hist;
     DevBuf<int> thr_bin;
     int frontier_grid = 0;             // CTAs of the cooperative launch (= what fits on the chip)
+    int optimize_grid = 0;             // resident CTAs of k_optimize
     unsigned long long* h_counters = nullptr;   // pinned
     unsigned long long* h_mirror = nullptr;     // pinned + mapped: HostMirror
     std::vector<cudaEvent_t> ev_pool;
@@ -371,7 +373,7 @@ __global__ void k_import_rgb(const uint8_t* __restrict__ src, int w, int h, int 
 
 // mve::image::rescale_half_size_gaussian<uint8_t>(img, 1.f) (image_tools.h:617-694) with Accum<uint8>
 // (accum.h:117-170): same 16 taps in the same order, fp32 accumulate, true division, math::round.
-// Bit-exact with the reference (tests/test_pyramid.py); products and sums are kept un-fused on purpose.
+// Bit-exact with the reference (tests/test_gpu_parity.py::test_pyramid_bit_exact); products and sums are kept un-fused on purpose.
 __global__ void k_half_gaussian(const uchar4* __restrict__ in, int iw, int ih, int ipitch,
                                 uchar4* __restrict__ out, int ow, int oh, int opitch,
                                 float w1, float w2, float w3)
@@ -405,6 +407,21 @@ __global__ void k_half_gaussian(const uchar4* __restrict__ in, int iw, int ih, i
     out[(size_t)y * opitch + x] = o;
 }
 
+// The bilinear footprint of a sample at (x + fx, y + fy) is the 2x2 block {(x,y), (x+1,y), (x,y+1), (x+1,y+1)}
+// (mvs_tools.cc:110-124): stored contiguously per (x, y) it is ONE aligned 16-byte load instead of four 4-byte ones.
+__global__ void k_make_quads(const uchar4* __restrict__ img, int w, int h, int pitch, uint4* __restrict__ quad)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    const int x1 = min(x + 1, w - 1), y1 = min(y + 1, h - 1);
+    const unsigned* p = reinterpret_cast<const unsigned*>(img);
+    uint4 q;
+    q.x = p[(size_t)y * pitch + x]; q.y = p[(size_t)y * pitch + x1];
+    q.z = p[(size_t)y1 * pitch + x]; q.w = p[(size_t)y1 * pitch + x1];
+    quad[(size_t)y * pitch + x] = q;
+}
+
 __global__ void k_export_rgb(const uchar4* __restrict__ src, int w, int h, int pitch, uint8_t* __restrict__ dst)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
@@ -418,42 +435,83 @@ __global__ void k_export_rgb(const uchar4* __restrict__ src, int w, int h, int p
 // ------------------------------------------------------------------------------------------------
 // kernels: patch optimisation + frontier
 // ------------------------------------------------------------------------------------------------
-#ifndef OPT_WARPS_PER_BLOCK
-#define OPT_WARPS_PER_BLOCK 4
+#ifndef OPT_TPB
+#define OPT_TPB 256          // threads per CTA of the patch-optimisation kernels (32 patch groups of 8 lanes)
 #endif
-constexpr int OPT_WARPS = OPT_WARPS_PER_BLOCK;
 #ifndef OPT_MIN_BLOCKS
-#define OPT_MIN_BLOCKS 5     // registers per thread <= 65536 / (OPT_MIN_BLOCKS * 128) -> 96; tuned on B200, profiles/r1_notes.md
+#define OPT_MIN_BLOCKS 2     // CTAs per SM: registers per thread <= 65536 / (OPT_MIN_BLOCKS * OPT_TPB); shared memory 80 KB per CTA
 #endif
+constexpr int OPT_WARPS = OPT_TPB / 32;
+// dynamic shared memory of the kernels that optimise patches: the replicated sRGB table + the per-thread arrays of Patch
+constexpr size_t OPT_SMEM_BYTES = sizeof(float) * (256 * LUT_REP + PRIV_WORDS * OPT_TPB);
+using PatchT = Patch<OPT_TPB>;
 
-// One warp per queue entry: PatchOptimization ctor + doAutoOptimization + computeConfidence.
-// (An 8-lanes-per-patch mapping was tried: 28 % fewer instructions but 4x the loop body, i-cache misses and a 75 % L1
-// hit rate made it 14 % slower - profiles/r1_notes.md.)
-constexpr int OPT_ENTRIES_PER_BLOCK = OPT_WARPS;
-__global__ void __launch_bounds__(OPT_WARPS * 32, OPT_MIN_BLOCKS)
-k_optimize(const Entry* __restrict__ in, PatchOut* __restrict__ out, const unsigned long long* n_ptr, int n_max,
+__device__ __forceinline__ Entry load_entry(const Entry* p)       // lists are rewritten by other SMs every round: bypass L1
+{
+    const int4 a = __ldcg(reinterpret_cast<const int4*>(p));
+    const int4 b = __ldcg(reinterpret_cast<const int4*>(p) + 1);
+    Entry e;
+    e.xy = a.x; e.jobdir = a.y; e.conf = __int_as_float(a.z); e.depth = __int_as_float(a.w);
+    e.dzI = __int_as_float(b.x); e.dzJ = __int_as_float(b.y); e.slots = (unsigned)b.z; e.pad = b.w;
+    return e;
+}
+
+// Fills the shared memory of a patch-optimisation kernel and binds the thread to its 8-lane group.
+__device__ __forceinline__ void opt_setup(PatchT& p, float* smem, const float* g_lut, const DevSettings* st, const ViewParams* views)
+{
+    for (int i = threadIdx.x; i < 256 * LUT_REP; i += blockDim.x) smem[i] = g_lut[i / LUT_REP];
+    __syncthreads();
+    bind_thread(p, st, views, smem, smem + 256 * LUT_REP, (int)threadIdx.x);
+}
+
+// The PatchOptimizations of list[0..n): every 8-lane group takes entries through the ticket counter until none is left; a
+// group that finishes one fetches the next at once, the other groups of its warp meet it again at the pass() call site
+// inside Patch::step().  PatchOptimization ctor + doAutoOptimization + computeConfidence per entry.
+__device__ __forceinline__ void optimise_entries(PatchT& p, const Entry* list, PatchOut* res, unsigned long long n,
+                                                 unsigned long long* ticket, const JobParams* jobs, unsigned long long* counters)
+{
+    bool have = false;
+    unsigned long long idx = 0ull;
+    unsigned opts = 0u;
+    for (;;) {
+        if (!have) {
+            unsigned long long w = 0ull;
+            if (p.gl == 0) w = atomicAdd(ticket, 1ull);
+            w = p.gbcast(w, 0);
+            if (w >= n) break;
+            idx = w;
+            const Entry e = load_entry(&list[w]);
+            PatchIn pi;
+            pi.x = e.xy & 0xFFFF; pi.y = (e.xy >> 16) & 0xFFFF;
+            pi.depth = e.depth; pi.dzI = e.dzI; pi.dzJ = e.dzJ; pi.slots = e.slots;
+            p.begin(&jobs[e.jobdir & 0xFFFFFF], pi);
+            have = true;
+            ++opts;
+        }
+        if (p.step()) {
+            PatchOut po;
+            p.finish(po);
+            if (p.gl == 0) res[idx] = po;
+            have = false;
+        }
+    }
+    if (p.gl == 0 && opts) {
+        atomicAdd(&counters[C_SETS], (unsigned long long)p.n_sets);
+        atomicAdd(&counters[C_OPTS], (unsigned long long)opts);
+        p.n_sets = 0u;
+    }
+}
+
+// A batch of independent PatchOptimizations (b200mvs_optimize_patches).
+__global__ void __launch_bounds__(OPT_TPB, OPT_MIN_BLOCKS)
+k_optimize(const Entry* __restrict__ in, PatchOut* __restrict__ out, int n,
            const DevSettings* __restrict__ st, const JobParams* __restrict__ jobs, const ViewParams* __restrict__ views,
            const float* __restrict__ g_lut, unsigned long long* counters)
 {
-    __shared__ float lut[256];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = g_lut[i];
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int eid = blockIdx.x * OPT_ENTRIES_PER_BLOCK + (threadIdx.x >> 5);
-    const int n = n_ptr ? (int)min((unsigned long long)n_max, *n_ptr) : n_max;
-    if (eid >= n) return;
-    const Entry e = in[eid];
-    PatchIn pi;
-    pi.x = e.xy & 0xFFFF; pi.y = (e.xy >> 16) & 0xFFFF;
-    pi.depth = e.depth; pi.dzI = e.dzI; pi.dzJ = e.dzJ; pi.slots = e.slots;
-    const JobParams* job = &jobs[e.jobdir & 0xFFFFFF];
-    PatchOut po;
-    const unsigned sets = optimize_patch(st, job, views, lut, lane, pi, po);
-    if (lane == 0) {
-        out[eid] = po;
-        atomicAdd(&counters[C_SETS], (unsigned long long)sets);
-        atomicAdd(&counters[C_OPTS], 1ull);
-    }
+    extern __shared__ float smem[];
+    PatchT p;
+    opt_setup(p, smem, g_lut, st, views);
+    optimise_entries(p, in, out, (unsigned long long)n, &counters[C_TICKET], jobs, counters);
 }
 
 __device__ __forceinline__ unsigned long long entry_key(const Entry& e)
@@ -520,15 +578,6 @@ __device__ __forceinline__ int conf_bin(float c)
     const int b = (int)(c * (float)HIST_FINE);
     return b < 0 ? 0 : (b > HIST_FINE - 1 ? HIST_FINE - 1 : b);
 }
-__device__ __forceinline__ Entry load_entry(const Entry* p)       // lists are rewritten by other SMs every round: bypass L1
-{
-    const int4 a = __ldcg(reinterpret_cast<const int4*>(p));
-    const int4 b = __ldcg(reinterpret_cast<const int4*>(p) + 1);
-    Entry e;
-    e.xy = a.x; e.jobdir = a.y; e.conf = __int_as_float(a.z); e.depth = __int_as_float(a.w);
-    e.dzI = __int_as_float(b.x); e.dzJ = __int_as_float(b.y); e.slots = (unsigned)b.z; e.pad = b.w;
-    return e;
-}
 __device__ __forceinline__ PatchOut load_result(const PatchOut* p)  // written by another SM in the optimise phase: bypass L1
 {
     static_assert(sizeof(PatchOut) == 40, "PatchOut layout");
@@ -552,30 +601,6 @@ __device__ __forceinline__ void write_pixel(const JobParams& J, int idx, const P
     J.dz[2 * idx] = r.dzI; J.dz[2 * idx + 1] = r.dzJ;
     J.normal[3 * idx] = r.nx; J.normal[3 * idx + 1] = r.ny; J.normal[3 * idx + 2] = r.nz;
     J.slots[idx] = r.slots;
-}
-
-// Warps take patches of run[0..n) through the ticket counter until none is left.
-__device__ __forceinline__ void optimise_phase(const FrontierParams& P, unsigned long long n, const float* lut, int lane)
-{
-    unsigned sets = 0u, opts = 0u;
-    for (;;) {
-        unsigned long long w = 0ull;
-        if (lane == 0) w = atomicAdd(&P.ctl->ticket, 1ull);
-        w = __shfl_sync(FULL, w, 0);
-        if (w >= n) break;
-        const Entry e = load_entry(&P.run[w]);
-        PatchIn pi;
-        pi.x = e.xy & 0xFFFF; pi.y = (e.xy >> 16) & 0xFFFF;
-        pi.depth = e.depth; pi.dzI = e.dzI; pi.dzJ = e.dzJ; pi.slots = e.slots;
-        PatchOut po;
-        sets += optimize_patch(P.st, &P.jobs[e.jobdir & 0xFFFFFF], P.views, lut, lane, pi, po);
-        ++opts;
-        if (lane == 0) P.res[w] = po;
-    }
-    if (lane == 0 && opts) {
-        atomicAdd(&P.counters[C_SETS], (unsigned long long)sets);
-        atomicAdd(&P.counters[C_OPTS], (unsigned long long)opts);
-    }
 }
 
 // Eligibility threshold of one job from its confidence histogram (one warp).  topk: the largest bin t such that at least
@@ -632,12 +657,12 @@ __device__ __forceinline__ int threshold_of(const unsigned* hist, int lane, int 
     return t_top > t_band ? t_top : t_band;
 }
 
-__global__ void __launch_bounds__(OPT_WARPS * 32, OPT_MIN_BLOCKS)
+__global__ void __launch_bounds__(OPT_TPB, OPT_MIN_BLOCKS)
 k_frontier(const FrontierParams P)
 {
-    __shared__ float lut[256];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = P.lut[i];
-    __syncthreads();
+    extern __shared__ float smem[];
+    PatchT patch;
+    opt_setup(patch, smem, P.lut, P.st, P.views);
     const int lane = threadIdx.x & 31;
     const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, gthreads = (size_t)gridDim.x * blockDim.x;
     FrontierCtl* const ctl = P.ctl;
@@ -721,7 +746,7 @@ k_frontier(const FrontierParams P)
         if (lead) ctl->nlist[p] = 0ull;                           // consumed; the round after the next pushes into it
         }
         // the PatchOptimizations of the round
-        optimise_phase(P, n_run, lut, lane);
+        optimise_entries(patch, P.run, P.res, n_run, &ctl->ticket, P.jobs, cnt);
         if (seed_round) {
             PHASE_END(PH_SEED);
             for (size_t i = gtid; i < (size_t)P.n_seeds; i += gthreads) {
@@ -886,14 +911,16 @@ int upload_common(b200mvs_ctx* ctx, int id, const uint8_t* d_src, int w, int h, 
     }
     size_t total = 0;
     for (HostLevel& L : v.lv) total += (size_t)L.pitch * L.h;
-    if (!v.d_base || v.bytes != total * sizeof(uchar4)) {
+    const size_t need = total * (sizeof(uchar4) + sizeof(uint4));
+    if (!v.d_base || v.bytes != need) {
         if (v.d_base) { cudaFree(v.d_base); v.d_base = nullptr; }
-        CK(cudaMalloc(&v.d_base, total * sizeof(uchar4)));
-        v.bytes = total * sizeof(uchar4);
+        CK(cudaMalloc(&v.d_base, need));
+        v.bytes = need;
         ctx->views_dirty = true;
     }
     size_t off = 0;
-    for (HostLevel& L : v.lv) { L.d_img = v.d_base + off; off += (size_t)L.pitch * L.h; }
+    uint4* qbase = reinterpret_cast<uint4*>(v.d_base + total);      // total is a multiple of 4 texels: 16-byte aligned
+    for (HostLevel& L : v.lv) { L.d_img = v.d_base + off; L.d_quad = qbase + off; off += (size_t)L.pitch * L.h; }
     const dim3 blk(32, 8);
     k_import_rgb<<<dim3((w + 31) / 32, (h + 7) / 8), blk, 0, stream>>>(d_src, w, h, ch, v.lv[0].d_img, v.lv[0].pitch);
     // ensureImages (image_pyramid.cc:56-95): rescale_half_size_gaussian(img, 1.f) level by level
@@ -903,6 +930,8 @@ int upload_common(b200mvs_ctx* ctx, int id, const uint8_t* d_src, int w, int h, 
         const HostLevel& b = v.lv[i];
         k_half_gaussian<<<dim3((b.w + 31) / 32, (b.h + 7) / 8), blk, 0, stream>>>(a.d_img, a.w, a.h, a.pitch, b.d_img, b.w, b.h, b.pitch, w1, w2, w3);
     }
+    for (const HostLevel& L : v.lv)
+        k_make_quads<<<dim3((L.w + 31) / 32, (L.h + 7) / 8), blk, 0, stream>>>(L.d_img, L.w, L.h, L.pitch, L.d_quad);
     CK(cudaGetLastError());
     v.valid = true;
     v.has_image = true;
@@ -929,6 +958,7 @@ int sync_view_params(b200mvs_ctx* ctx)
             const HostLevel& L = v.lv[l];
             p.lv[l].ax = L.proj[0]; p.lv[l].ay = L.proj[4]; p.lv[l].cx = L.proj[2]; p.lv[l].cy = L.proj[5];
             p.lv[l].w = L.w; p.lv[l].h = L.h; p.lv[l].pitch = L.pitch; p.lv[l].img = v.has_image ? L.d_img : nullptr;
+            p.lv[l].quad = v.has_image ? L.d_quad : nullptr;
         }
     }
     CK(cudaMemcpyAsync(ctx->d_views, hp.data(), hp.size() * sizeof(ViewParams), cudaMemcpyHostToDevice, ctx->stream));
@@ -941,6 +971,22 @@ cudaEvent_t get_event(b200mvs_ctx* ctx, size_t i)
 {
     while (ctx->ev_pool.size() <= i) { cudaEvent_t e; cudaEventCreate(&e); ctx->ev_pool.push_back(e); }
     return ctx->ev_pool[i];
+}
+
+// Opt-in to > 48 KB of dynamic shared memory and size the grids to what is resident on the chip (once per context).
+int prepare_kernels(b200mvs_ctx* ctx)
+{
+    if (ctx->frontier_grid) return 0;
+    CK(cudaFuncSetAttribute(k_frontier, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OPT_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(k_optimize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OPT_SMEM_BYTES));
+    int per_sm = 0, per_sm_opt = 0, sms = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_frontier, OPT_TPB, OPT_SMEM_BYTES));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_opt, k_optimize, OPT_TPB, OPT_SMEM_BYTES));
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+    if (per_sm < 1 || per_sm_opt < 1) return fail(ctx, B200MVS_ERR_CUDA, "patch-optimisation kernels do not fit on an SM");
+    ctx->optimize_grid = per_sm_opt * sms;
+    ctx->frontier_grid = per_sm * sms;
+    return 0;
 }
 
 // JobParams of one reference view (everything except the map pointers)
@@ -1025,7 +1071,7 @@ int b200mvs_create(int device, int n_views, b200mvs_ctx** out)
     if ((e = cudaMalloc(&ctx->d_lut, 256 * sizeof(float))) != cudaSuccess) return bail("cudaMalloc(lut)", e);
     if ((e = cudaMallocHost(&ctx->h_counters, sizeof(unsigned long long) * 4096)) != cudaSuccess) return bail("cudaMallocHost", e);
     if ((e = cudaHostAlloc(&ctx->h_mirror, sizeof(unsigned long long) * 4200, cudaHostAllocMapped)) != cudaSuccess) return bail("cudaHostAlloc", e);
-    // sRGB code value -> linear: the formula documented at mvs_tools.cc:21-29; tests/test_lut.py checks the
+    // sRGB code value -> linear: the formula documented at mvs_tools.cc:21-29; tests/test_oracle_vs_reference.py::test_srgb_table_matches_reference checks the
     // 256 floats against the reference table.
     float lut[256];
     for (int i = 0; i < 256; ++i) {
@@ -1218,8 +1264,14 @@ int b200mvs_optimize_patches(b200mvs_ctx* ctx, const b200mvs_settings* s, int re
     CK(cudaMemsetAsync(ctx->counters.p, 0, sizeof(unsigned long long) * C_NUM, st));
     cudaEvent_t e0 = get_event(ctx, 0), e1 = get_event(ctx, 1);
     CK(cudaEventRecord(e0, st));
-    k_optimize<<<(n + OPT_ENTRIES_PER_BLOCK - 1) / OPT_ENTRIES_PER_BLOCK, OPT_WARPS * 32, 0, st>>>(ctx->run_in.p, ctx->run_out.p, nullptr, n, ctx->d_settings.p,
-                                                                         ctx->d_jobs.p, ctx->d_views, ctx->d_lut, ctx->counters.p);
+    {
+        int rc2 = prepare_kernels(ctx);
+        if (rc2) return rc2;
+        const int groups_per_block = OPT_TPB / GROUP;
+        const int grid = std::max(1, std::min((n + groups_per_block - 1) / groups_per_block, ctx->optimize_grid));
+        k_optimize<<<grid, OPT_TPB, OPT_SMEM_BYTES, st>>>(ctx->run_in.p, ctx->run_out.p, n, ctx->d_settings.p,
+                                                          ctx->d_jobs.p, ctx->d_views, ctx->d_lut, ctx->counters.p);
+    }
     CK(cudaGetLastError());
     CK(cudaEventRecord(e1, st));
     std::vector<PatchOut> ho(n);
@@ -1395,18 +1447,12 @@ int b200mvs_reconstruct(b200mvs_ctx* ctx, const b200mvs_settings* s, int n_refs,
                 return fail(ctx, B200MVS_ERR_CANCELLED, "reconstruction cancelled");
             }
     // ---- one cooperative launch: seeds + all frontier rounds (DESIGN.md "Frontier schedule") ----
-    if (ctx->frontier_grid == 0) {
-        int per_sm = 0, sms = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_frontier, OPT_WARPS * 32, 0));
-        CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
-        if (per_sm < 1) return fail(ctx, B200MVS_ERR_CUDA, "k_frontier does not fit on an SM");
-        ctx->frontier_grid = per_sm * sms;
-    }
+    if ((rc = prepare_kernels(ctx))) return rc;
     cudaEvent_t ev_begin = get_event(ctx, 0), ev_end = get_event(ctx, 1);
     CK(cudaEventRecord(ev_begin, st));
     {
         void* args[] = {(void*)&P};
-        CK(cudaLaunchCooperativeKernel((const void*)k_frontier, dim3(ctx->frontier_grid), dim3(OPT_WARPS * 32), args, 0, st));
+        CK(cudaLaunchCooperativeKernel((const void*)k_frontier, dim3(ctx->frontier_grid), dim3(OPT_TPB), args, OPT_SMEM_BYTES, st));
     }
     CK(cudaEventRecord(ev_end, st));
     CK(cudaMemcpyAsync(ctx->h_counters, ctx->counters.p, sizeof(unsigned long long) * (C_NUM + n_refs), cudaMemcpyDeviceToHost, st));

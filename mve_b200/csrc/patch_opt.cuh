@@ -1,4 +1,5 @@
-// Device-side patch optimisation: one warp per patch, lane k < 25 owns sample k of the 5x5 patch.
+// Device-side patch optimisation: EIGHT lanes per patch (four patches per warp), each lane owning up to four of the
+// 25 samples of the 5x5 patch.
 //
 // Restates, for the GPU, what one mvs::PatchOptimization does in the reference
 // (libs/dmrecon/patch_optimization.cc:21-364 with PatchSampler patch_sampler.cc:19-393,
@@ -11,13 +12,21 @@
 //     selected views that draws the fused sample set and immediately reduces it to what the reference
 //     reads at that state - NCC of the view (getFastNCC), the colour-scale update when one is due
 //     (computeColorScale), and the Gauss-Newton terms of the next step (optimizeDepthOnly /
-//     optimizeDepthAndNormal).  Nothing per-sample survives a pass, so the loop body exists once in
-//     the instruction stream (the first version inlined 16 copies and stalled on instruction fetch,
-//     profiles/r1_notes.md);
-//   * small per-view arrays (selected slots, colour scales, NCCs) live one element per lane and are
-//     read with warp shuffles; sums over the 25 samples are (batched) warp-shuffle butterflies; the
-//     sums of the 3x3 normal equations (patch_optimization.cc:326-343) are formed per lane in fp32
-//     (<= 12 products) and across the lanes in fp64, then solved in fp64 inside the pass.
+//     optimizeDepthAndNormal);
+//   * a group of 8 lanes is an independent unit: every collective names only the group's lanes, so the four
+//     groups of a warp run different patches, in different stages, and re-converge at the one pass() call
+//     site; a group that finishes fetches its next patch without waiting for the others (Patch::begin /
+//     step / finish are driven by a flat loop in the kernels);
+//   * the loop over a lane's sample slots is ROLLED (the sampling code exists once in the instruction
+//     stream, profiles/r1_notes.md explains why that matters); what must survive between the slots of a
+//     sample set - rays, master colours, the drawn colours and derivatives - lives in shared memory,
+//     one word per thread and array element, bank-conflict free;
+//   * the four bilinear taps of a sample come from ONE 16-byte load of a "quad" texel (the 2x2 neighbourhood
+//     of every pixel is stored contiguously, DESIGN.md "Data layout"); sRGB code values are linearised through a
+//     copy of the 256-entry table that is replicated per lane (no bank conflicts, mvs_tools.cc:21-95);
+//   * small per-view arrays (selected slots, colour scales, NCCs) live one element per lane of the group and are
+//     read with shuffles; the sums of the 3x3 normal equations (patch_optimization.cc:326-343) are formed
+//     per lane in fp32 (<= 16 products) and across the lanes in fp64, then solved in fp64 inside the pass.
 #pragma once
 #if defined(B200MVS_HOST_EMU)
 #include "simt_emu.h"      // tests/emu: runs this very file on the CPU, 32 host threads per warp (test infrastructure)
@@ -35,14 +44,19 @@ constexpr int MAX_LOCAL = 4;
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int NS = 25;
 constexpr int CENTER = 12;   // patch_sampler.cc:73,96
+constexpr int GROUP = 8;     // lanes per patch
+constexpr int SLOTS = 4;     // sample slots per lane: slot 0 = samples 24.. (+ two helper points), slot s = samples 8(s-1)..8(s-1)+7
+constexpr int LUT_REP = 32;  // replicas of the sRGB table in shared memory (one per lane)
+// per-thread words in shared memory (element e of thread t at priv[e * TPB + t])
+constexpr int PW_RAY = 0, PW_M = 12, PW_N = 24, PW_D = 36, PRIV_WORDS = 48;
 
 struct alignas(16) LevelParams {   // ImagePyramidLevel (image_pyramid.h:28-59): K = [ax 0 cx; 0 ay cy; 0 0 1]
     float ax, ay, cx, cy;
     int w, h;
-    int pitch;                // in texels (uchar4)
+    int pitch;                // in texels (uchar4), also the pitch of the quad image (uint4)
     int pad;
     const uchar4* img;        // RGBX8, row pitch 16-byte aligned
-    unsigned long long pad2;
+    const uint4* quad;        // quad[y * pitch + x] = {img(x,y), img(x+1,y), img(x,y+1), img(x+1,y+1)} (clamped at the border)
 };
 static_assert(sizeof(LevelParams) == 48, "LevelParams layout");
 
@@ -80,30 +94,10 @@ struct PatchIn  { int x, y; float depth, dzI, dzJ; unsigned slots; };   // slots
 struct PatchOut { float conf, depth, dzI, dzJ, nx, ny, nz; unsigned slots; int iterations; int flags; };
 // flags: bit0 converged, bit1 opti_success
 
-__device__ __forceinline__ float warp_sum(float v)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-    return v;
-}
-__device__ __forceinline__ double warp_sum(double v)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-    return v;
-}
-__device__ __forceinline__ float warp_max(float v)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL, v, o));
-    return v;
-}
-
 // Hot-path approximations (each <= 2 ulp): MUFU reciprocal / reciprocal square root instead of the IEEE division and
-// square root sequences (which cost ~10 instructions + a slow-path branch each and made up ~16 % of the kernel).  The
-// reference itself is built with -funsafe-math-optimizations (Makefile.inc:5), i.e. without IEEE guarantees for these
-// operations; the effect on parity is measured by tests/test_gpu_parity.py.  Everything that decides integers on the
-// host (global view selection, seeds, pyramid) stays IEEE.
+// square root sequences.  The reference itself is built with -funsafe-math-optimizations (Makefile.inc:5), i.e. without
+// IEEE guarantees for these operations; the effect on parity is measured by tests/test_gpu_parity.py.  Everything that
+// decides integers on the host (global view selection, seeds, pyramid) stays IEEE.
 #if defined(B200MVS_HOST_EMU)
 __device__ __forceinline__ float rcp_fast(float x) { return 1.f / x; }
 __device__ __forceinline__ float rsqrt_fast(float x) { return 1.f / sqrtf(x); }
@@ -112,53 +106,22 @@ __device__ __forceinline__ float rcp_fast(float x) { float r; asm("rcp.approx.ft
 __device__ __forceinline__ float rsqrt_fast(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 #endif
 
-// Batched butterflies: reducing K values together halves the number of live values at each of the first log2(K)
-// steps, so 4 sums cost 10 shuffles instead of 20 (2 sums: 7 instead of 10).  Every lane receives all totals, and all
-// lanes receive bitwise identical totals (each total is formed in exactly one lane group and then broadcast).
-__device__ __forceinline__ void warp_sum4(int lane, float& a, float& b, float& c, float& d)
-{
-    const bool h16 = lane & 16, h8 = lane & 8;
-    float k0 = h16 ? c : a, k1 = h16 ? d : b;
-    const float s0 = h16 ? a : c, s1 = h16 ? b : d;
-    k0 += __shfl_xor_sync(FULL, s0, 16);
-    k1 += __shfl_xor_sync(FULL, s1, 16);
-    float k = h8 ? k1 : k0;
-    const float s = h8 ? k0 : k1;
-    k += __shfl_xor_sync(FULL, s, 8);
-    k += __shfl_xor_sync(FULL, k, 4);
-    k += __shfl_xor_sync(FULL, k, 2);
-    k += __shfl_xor_sync(FULL, k, 1);
-    a = __shfl_sync(FULL, k, 0); b = __shfl_sync(FULL, k, 8); c = __shfl_sync(FULL, k, 16); d = __shfl_sync(FULL, k, 24);
-}
-__device__ __forceinline__ void warp_sum2(int lane, float& a, float& b)
-{
-    const bool h16 = lane & 16;
-    float k = h16 ? b : a;
-    const float s = h16 ? a : b;
-    k += __shfl_xor_sync(FULL, s, 16);
-    k += __shfl_xor_sync(FULL, k, 8);
-    k += __shfl_xor_sync(FULL, k, 4);
-    k += __shfl_xor_sync(FULL, k, 2);
-    k += __shfl_xor_sync(FULL, k, 1);
-    a = __shfl_sync(FULL, k, 0); b = __shfl_sync(FULL, k, 16);
-}
-
+// TPB = threads per block (stride of the per-thread arrays in shared memory)
+template <int TPB>
 struct Patch {
-    // ---- constants of the patch ----
+    // ---- constants of the thread ----
     const DevSettings* st;
-    const JobParams* job;
     const ViewParams* views;
+    const float* lutw;         // replicated srgb2lin table + lane: value v of this lane at lutw[v * LUT_REP]
+    float* priv;               // this thread's column of the per-thread arrays
+    int gl;                    // lane within the group
+    unsigned gmask;            // lanes of the group
+    // ---- constants of the patch ----
+    const JobParams* job;
     const ViewParams* rv;
-    const float* lut;          // srgb2lin in shared memory (mvs_tools.cc:21-95)
-    int lane;
-    bool act;                  // lane < 25
-    float fi, fj;              // sample offsets (patch_optimization.cc:56-64)
-    // ---- per-lane sample state ----
-    float rx, ry, rz;          // masterViewDirs[k]
-    float px, py, pz;          // patchPoints[k]
-    float m0, m1, m2;          // masterColorSamples[k] (normalised)
-    float e0, e1, e2;          // masterColorSamples[k] - meanX
-    // ---- warp-uniform state ----
+    int x0, y0;
+    // ---- group-uniform state ----
+    float mx0, mx1, mx2;       // meanX per channel (patch_sampler.cc:333-339)
     float crx, cry, crz;       // masterViewDirs[12]
     float cpx, cpy, cpz;       // patchPoints[12]
     float mfp, inv_mfp;        // footPrintScaled(patchPoints[12]) and its reciprocal
@@ -170,21 +133,60 @@ struct Patch {
     int iter;
     bool opti, converged, lvs_ok;
     unsigned n_sets;
-    // ---- lane-distributed small arrays: lane k (< nsel) holds element k ----
+    // state machine of doAutoOptimization
+    int stage;
+    bool viewRemoved, was_normal, normal;
+    float old;                 // oldNCC of selected view `gl`
+    // ---- lane-distributed small arrays: lane k (< nsel) of the group holds element k ----
     int sel_l;                 // selected global slot (ascending over lanes)
     float cs0_l, cs1_l, cs2_l; // colorScale of selected view k
     float ncc_l;               // NCC of selected view k at the state of the last pass
+    float cand0, cand1, cand2, cand3;   // NCC of candidate global slot gl + 8 j (local view selection)
     // ---- results of the last pass (valid for the current state and selected set) ----
     unsigned p_col_ok, p_der_ok;   // bit k: colour / derivative path of selected view k succeeded
     float p_num, p_den;            // optimizeDepthOnly sums
     float nX0, nX1, nX2;           // solution of the 3x3 normal equations of optimizeDepthAndNormal
     bool n_singular;               // detATA == 0 (patch_optimization.cc:347-351)
     bool p_has_normal, p_has_ncc;
-    float cand_ncc_l;          // NCC of candidate global slot `lane` (local view selection)
+
+    enum Stage { LVS_CTOR, CTOR, FIRST, PRE, POST, LVS_REPL, REPL, DONE };
+
+    // ---- group collectives ----
+    template <typename T> __device__ __forceinline__ T gbcast(T v, int src) const { return __shfl_sync(gmask, v, src, GROUP); }
+    __device__ __forceinline__ float gsum(float v) const
+    {
+#pragma unroll
+        for (int o = GROUP / 2; o > 0; o >>= 1) v += __shfl_xor_sync(gmask, v, o);
+        return v;
+    }
+    __device__ __forceinline__ double gsum(double v) const
+    {
+#pragma unroll
+        for (int o = GROUP / 2; o > 0; o >>= 1) v += __shfl_xor_sync(gmask, v, o);
+        return v;
+    }
+    __device__ __forceinline__ float gmax(float v) const
+    {
+#pragma unroll
+        for (int o = GROUP / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(gmask, v, o));
+        return v;
+    }
+    __device__ __forceinline__ bool gany(bool p) const { return __any_sync(gmask, p) != 0; }
+    __device__ __forceinline__ unsigned gballot(bool p) const      // bit k = lane k of the group
+    {
+        const unsigned b = __ballot_sync(gmask, p) & gmask;
+        return (b >> (__ffs(gmask) - 1)) & 0xFFu;
+    }
+
+    // ---- per-thread arrays in shared memory ----
+    __device__ __forceinline__ float& pw(int e) const { return priv[e * TPB]; }
+
+    // sample handled by (slot s, this lane): index, kind and patch offsets (patch_optimization.cc:56-64)
+    __device__ __forceinline__ int sample_index(int s) const { return s == 0 ? 24 + gl : (s - 1) * GROUP + gl; }
+    __device__ __forceinline__ bool is_real(int s) const { return s != 0 || gl == 0; }
 
     // single_view.h:188-195 (K has the sparsity of camera.cc:125-144).  x = (K cp).x / cp.z - 0.5 is evaluated with one
-    // correctly rounded reciprocal shared by x and y (<= 1 ulp from the reference's two divisions; measured effect on
-    // parity in tests/test_gpu_parity.py).
+    // reciprocal shared by x and y (<= 2 ulp from the reference's two divisions).
     __device__ __forceinline__ void project(const float (&w)[12], const LevelParams& L, float X, float Y, float Z,
                                             float& x, float& y) const
     {
@@ -199,15 +201,18 @@ struct Patch {
     // patch_sampler.cc:274-295 (+ the centre point / master footprint used by every sample set)
     __device__ __forceinline__ void compute_points()
     {
-        const float t = depth + fi * dzI + fj * dzJ;
-        const bool bad = act && (t <= 0.f);
-        if (__any_sync(FULL, bad)) ref_ok = false;
-        px = __ldg(&rv->campos[0]) + t * rx;
-        py = __ldg(&rv->campos[1]) + t * ry;
-        pz = __ldg(&rv->campos[2]) + t * rz;
-        cpx = __shfl_sync(FULL, px, CENTER);
-        cpy = __shfl_sync(FULL, py, CENTER);
-        cpz = __shfl_sync(FULL, pz, CENTER);
+        bool bad = false;
+#pragma unroll 1
+        for (int s = 0; s < SLOTS; ++s) {
+            const int k = sample_index(s);
+            const float fi = (float)(k % 5 - 2), fj = (float)(k / 5 - 2);
+            const float t = depth + fi * dzI + fj * dzJ;
+            bad |= is_real(s) && (t <= 0.f);
+        }
+        if (gany(bad)) ref_ok = false;
+        cpx = __ldg(&rv->campos[0]) + depth * crx;       // the centre sample has offsets (0, 0): t = depth
+        cpy = __ldg(&rv->campos[1]) + depth * cry;
+        cpz = __ldg(&rv->campos[2]) + depth * crz;
         const float z = __ldg(&rv->w2c[8]) * cpx + __ldg(&rv->w2c[9]) * cpy + __ldg(&rv->w2c[10]) * cpz + __ldg(&rv->w2c[11]);
         mfp = z * job->ki0;     // single_view.h:160-164
         inv_mfp = rcp_fast(mfp);
@@ -216,38 +221,58 @@ struct Patch {
     // PatchSampler ctor (patch_sampler.cc:19-62) + computeMasterSamples (:298-345)
     __device__ __forceinline__ void init_sampler(int x, int y)
     {
-        act = lane < NS;
-        const int di = act ? (lane % 5) - 2 : 0, dj = act ? (lane / 5) - 2 : 0;
-        fi = (float)di; fj = (float)dj;
-        ref_ok = false; mm = 0.f; sqrDevX = 0.f; n_sets = 0u;
-        rx = ry = rz = px = py = pz = 0.f; m0 = m1 = m2 = e0 = e1 = e2 = 0.f;
+        ref_ok = false; mm = 0.f; sqrDevX = 0.f;
+        mx0 = mx1 = mx2 = 0.f;
         crx = cry = crz = cpx = cpy = cpz = mfp = inv_mfp = 0.f;
         if (x - 2 < 0 || y - 2 < 0 || x + 2 > job->W - 1 || y + 2 > job->H - 1) return;
-        // viewRayScaled (single_view.cc:99-106, depthmap.cc:149-156)
-        {
+        float sum = 0.f;
+#pragma unroll 1
+        for (int s = 0; s < SLOTS; ++s) {
+            const int k = sample_index(s);
+            const bool real = is_real(s);
+            const int di = real ? k % 5 - 2 : 0, dj = real ? k / 5 - 2 : 0;
+            // viewRayScaled (single_view.cc:99-106, depthmap.cc:149-156)
             const float fx = (float)(x + di) + 0.5f, fy = (float)(y + dj) + 0.5f;
             float vx = job->ki0 * fx + job->ki2;
             float vy = job->ki4 * fy + job->ki5;
             float vz = 1.0f;
             const float nrm = sqrtf(vx * vx + vy * vy + vz * vz);
             vx /= nrm; vy /= nrm; vz /= nrm;
-            rx = __ldg(&rv->rot[0]) * vx + __ldg(&rv->rot[3]) * vy + __ldg(&rv->rot[6]) * vz;
-            ry = __ldg(&rv->rot[1]) * vx + __ldg(&rv->rot[4]) * vy + __ldg(&rv->rot[7]) * vz;
-            rz = __ldg(&rv->rot[2]) * vx + __ldg(&rv->rot[5]) * vy + __ldg(&rv->rot[8]) * vz;
+            const float rx = __ldg(&rv->rot[0]) * vx + __ldg(&rv->rot[3]) * vy + __ldg(&rv->rot[6]) * vz;
+            const float ry = __ldg(&rv->rot[1]) * vx + __ldg(&rv->rot[4]) * vy + __ldg(&rv->rot[7]) * vz;
+            const float rz = __ldg(&rv->rot[2]) * vx + __ldg(&rv->rot[5]) * vy + __ldg(&rv->rot[8]) * vz;
+            pw(PW_RAY + 3 * s) = rx; pw(PW_RAY + 3 * s + 1) = ry; pw(PW_RAY + 3 * s + 2) = rz;
+            if (s == 2) {                                 // sample 12 = slot 2, lane 4
+                crx = gbcast(rx, CENTER - GROUP); cry = gbcast(ry, CENTER - GROUP); crz = gbcast(rz, CENTER - GROUP);
+            }
+            // master colours
+            float m0 = 0.f, m1 = 0.f, m2 = 0.f;
+            if (real) {
+                const uchar4 t = job->ref_img[(size_t)(y + dj) * job->ref_pitch + (x + di)];
+                m0 = lutw[t.x * LUT_REP]; m1 = lutw[t.y * LUT_REP]; m2 = lutw[t.z * LUT_REP];
+            }
+            pw(PW_M + 3 * s) = m0; pw(PW_M + 3 * s + 1) = m1; pw(PW_M + 3 * s + 2) = m2;
+            sum += m0 + m1 + m2;
         }
-        crx = __shfl_sync(FULL, rx, CENTER);
-        cry = __shfl_sync(FULL, ry, CENTER);
-        crz = __shfl_sync(FULL, rz, CENTER);
         ref_ok = true;
-        // master colours
-        const uchar4 t = job->ref_img[(size_t)(y + dj) * job->ref_pitch + (x + di)];
-        m0 = act ? lut[t.x] : 0.f; m1 = act ? lut[t.y] : 0.f; m2 = act ? lut[t.z] : 0.f;
-        mm = warp_sum(m0 + m1 + m2) / (3.f * NS);
+        mm = gsum(sum) / (3.f * NS);
         if (mm < 0.01f || mm > 0.99f) { ref_ok = false; return; }
-        m0 /= mm; m1 /= mm; m2 /= mm;
-        const float mx0 = warp_sum(m0) / (float)NS, mx1 = warp_sum(m1) / (float)NS, mx2 = warp_sum(m2) / (float)NS;
-        e0 = act ? m0 - mx0 : 0.f; e1 = act ? m1 - mx1 : 0.f; e2 = act ? m2 - mx2 : 0.f;
-        sqrDevX = warp_sum(e0 * e0 + e1 * e1 + e2 * e2);
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+        for (int s = 0; s < SLOTS; ++s) {
+            const float m0 = pw(PW_M + 3 * s) / mm, m1 = pw(PW_M + 3 * s + 1) / mm, m2 = pw(PW_M + 3 * s + 2) / mm;
+            pw(PW_M + 3 * s) = m0; pw(PW_M + 3 * s + 1) = m1; pw(PW_M + 3 * s + 2) = m2;
+            s0 += m0; s1 += m1; s2 += m2;                 // helper points hold 0
+        }
+        mx0 = gsum(s0) / (float)NS; mx1 = gsum(s1) / (float)NS; mx2 = gsum(s2) / (float)NS;
+        float dev = 0.f;
+#pragma unroll 1
+        for (int s = 0; s < SLOTS; ++s) {
+            if (!is_real(s)) continue;
+            const float e0 = pw(PW_M + 3 * s) - mx0, e1 = pw(PW_M + 3 * s + 1) - mx1, e2 = pw(PW_M + 3 * s + 2) - mx2;
+            dev += e0 * e0 + e1 * e1 + e2 * e2;
+        }
+        sqrDevX = gsum(dev);
         compute_points();
     }
 
@@ -260,11 +285,12 @@ struct Patch {
 
     // One fused sample set in view V at the current state: fastColAndDeriv (patch_sampler.cc:65-133 +
     // mvs_tools.cc:98-145) and computeNeighColorSamples (patch_sampler.cc:348-393 + mvs_tools.cc:169-199).
-    // Returns bit0 = colour path succeeded, bit1 = derivative path succeeded.
-    __device__ __forceinline__ unsigned sample(const ViewParams* V, float (&n)[3], float (&d)[3])
+    // Colours and derivatives of the lane's samples go to shared memory (PW_N, PW_D), sn receives the lane's partial
+    // colour sums.  Returns bit0 = colour path succeeded, bit1 = derivative path succeeded.
+    __device__ __forceinline__ unsigned sample(const ViewParams* V, float (&sn)[3])
     {
-        ++n_sets;
-        n[0] = n[1] = n[2] = 0.f; d[0] = d[1] = d[2] = 0.f;
+        if (gl == 0) ++n_sets;
+        sn[0] = sn[1] = sn[2] = 0.f;
         float w[12];
         {
             const float4 a = __ldg(reinterpret_cast<const float4*>(&V->w2c[0]));
@@ -288,62 +314,73 @@ struct Patch {
             const float4 k = __ldg(reinterpret_cast<const float4*>(&V->lv[l].ax));
             const int4 g = __ldg(reinterpret_cast<const int4*>(&V->lv[l].w));
             L.ax = k.x; L.ay = k.y; L.cx = k.z; L.cy = k.w; L.w = g.x; L.h = g.y; L.pitch = g.z;
-            L.img = reinterpret_cast<const uchar4*>(__ldg(reinterpret_cast<const unsigned long long*>(&V->lv[l].img)));
+            L.quad = reinterpret_cast<const uint4*>(__ldg(reinterpret_cast<const unsigned long long*>(&V->lv[l].quad)));
         }
-        // every lane projects its own patch point; the spare lane 25 projects patchPoints[12] + masterViewDirs[12]
-        // so that the derivative step (patch_sampler.cc:94-100) costs no extra instructions
-        const bool aux = lane == NS;
-        float qx, qy;
-        project(w, L, aux ? cpx + crx : px, aux ? cpy + cry : py, aux ? cpz + crz : pz, qx, qy);
-        const float ddx = __shfl_sync(FULL, qx, NS) - __shfl_sync(FULL, qx, CENTER);
-        const float ddy = __shfl_sync(FULL, qy, NS) - __shfl_sync(FULL, qy, CENTER);
-        const float dd2 = ddx * ddx + ddy * ddy;
-        const float dd = dd2 * rsqrt_fast(dd2);        // |.|; NaN for dd2 == 0, which fails `d > 0` like the reference's 0
-        const bool dok = dd > 0.f;
-        const float step = rcp_fast(dd);
-        const bool inb = qx > 0.f && qx < (float)(L.w - 1) && qy > 0.f && qy < (float)(L.h - 1);
-        if (!__all_sync(FULL, inb || !act)) return 0u;
-        if (act) {
-            float gx = 0.f, gy = 0.f;
-            if (dok) {
-                float tx, ty;
-                project(w, L, px + rx * step, py + ry * step, pz + rz * step, tx, ty);
-                gx = tx - qx; gy = ty - qy;
+        const float c0x = __ldg(&rv->campos[0]), c0y = __ldg(&rv->campos[1]), c0z = __ldg(&rv->campos[2]);
+        float dd = 0.f, step = 0.f;
+        bool dok = false, oob = false;
+#pragma unroll 1
+        for (int s = 0; s < SLOTS; ++s) {
+            const int k = sample_index(s);
+            const bool real = is_real(s);
+            const float rx = pw(PW_RAY + 3 * s), ry = pw(PW_RAY + 3 * s + 1), rz = pw(PW_RAY + 3 * s + 2);
+            float X, Y, Z;
+            if (s == 0 && gl != 0) {
+                // helper points of the derivative step (patch_sampler.cc:94-100): lane 1 projects
+                // patchPoints[12] + masterViewDirs[12], lane 2 patchPoints[12]
+                const float a = gl == 1 ? 1.f : 0.f;
+                X = cpx + a * crx; Y = cpy + a * cry; Z = cpz + a * crz;
+            } else {
+                const float t = depth + (float)(k % 5 - 2) * dzI + (float)(k / 5 - 2) * dzJ;
+                X = c0x + t * rx; Y = c0y + t * ry; Z = c0z + t * rz;
             }
-            const int left = (int)floorf(qx), top = (int)floorf(qy);
-            const float fx = qx - (float)left, fy = qy - (float)top;
-            const uchar4* r0 = L.img + (size_t)top * L.pitch + left;
-            const uchar4* r1 = r0 + L.pitch;
-            const uchar4 A = __ldg(r0), B = __ldg(r0 + 1), C = __ldg(r1), D = __ldg(r1 + 1);
-            const float a[3] = {lut[A.x], lut[A.y], lut[A.z]};
-            const float b[3] = {lut[B.x], lut[B.y], lut[B.z]};
-            const float c[3] = {lut[C.x], lut[C.y], lut[C.z]};
-            const float e[3] = {lut[D.x], lut[D.y], lut[D.z]};
+            float qx, qy;
+            project(w, L, X, Y, Z, qx, qy);
+            if (s == 0) {
+                const float ddx = gbcast(qx, 1) - gbcast(qx, 2);
+                const float ddy = gbcast(qy, 1) - gbcast(qy, 2);
+                const float dd2 = ddx * ddx + ddy * ddy;
+                dd = dd2 * rsqrt_fast(dd2);            // |.|; NaN for dd2 == 0, which fails `d > 0` like the reference's 0
+                dok = dd > 0.f;
+                step = rcp_fast(dd);
+            }
+            float n0 = 0.f, n1 = 0.f, n2 = 0.f, d0 = 0.f, d1 = 0.f, d2 = 0.f;
+            if (real) {
+                const bool inb = qx > 0.f && qx < (float)(L.w - 1) && qy > 0.f && qy < (float)(L.h - 1);
+                if (!inb) oob = true;
+                else {
+                    float gx = 0.f, gy = 0.f;
+                    if (dok) {
+                        float tx, ty;
+                        project(w, L, X + rx * step, Y + ry * step, Z + rz * step, tx, ty);
+                        gx = tx - qx; gy = ty - qy;
+                    }
+                    const int left = (int)floorf(qx), top = (int)floorf(qy);
+                    const float fx = qx - (float)left, fy = qy - (float)top;
+                    const uint4 Q = __ldg(L.quad + (size_t)top * L.pitch + left);
+                    float a[3], b[3], c[3], e[3];
+                    a[0] = lutw[(Q.x & 0xFF) * LUT_REP]; a[1] = lutw[((Q.x >> 8) & 0xFF) * LUT_REP]; a[2] = lutw[((Q.x >> 16) & 0xFF) * LUT_REP];
+                    b[0] = lutw[(Q.y & 0xFF) * LUT_REP]; b[1] = lutw[((Q.y >> 8) & 0xFF) * LUT_REP]; b[2] = lutw[((Q.y >> 16) & 0xFF) * LUT_REP];
+                    c[0] = lutw[(Q.z & 0xFF) * LUT_REP]; c[1] = lutw[((Q.z >> 8) & 0xFF) * LUT_REP]; c[2] = lutw[((Q.z >> 16) & 0xFF) * LUT_REP];
+                    e[0] = lutw[(Q.w & 0xFF) * LUT_REP]; e[1] = lutw[((Q.w >> 8) & 0xFF) * LUT_REP]; e[2] = lutw[((Q.w >> 16) & 0xFF) * LUT_REP];
+                    float nn[3], dv[3];
 #pragma unroll
-            for (int ch = 0; ch < 3; ++ch) {
-                const float x0 = (1.f - fx) * a[ch] + fx * b[ch];
-                const float x3 = (1.f - fx) * c[ch] + fx * e[ch];
-                n[ch] = (1.f - fy) * x0 + fy * x3;
-                const float der = gx * (b[ch] - a[ch]) + gy * (c[ch] - a[ch]) + (gy * fx + gx * fy) * (a[ch] - b[ch] - c[ch] + e[ch]);
-                d[ch] = dok ? der * dd : 0.f;        // deriv /= stepSize with stepSize = 1 / d (patch_sampler.cc:100,129-130)
+                    for (int ch = 0; ch < 3; ++ch) {
+                        const float x0 = (1.f - fx) * a[ch] + fx * b[ch];
+                        const float x3 = (1.f - fx) * c[ch] + fx * e[ch];
+                        nn[ch] = (1.f - fy) * x0 + fy * x3;
+                        const float der = gx * (b[ch] - a[ch]) + gy * (c[ch] - a[ch]) + (gy * fx + gx * fy) * (a[ch] - b[ch] - c[ch] + e[ch]);
+                        dv[ch] = dok ? der * dd : 0.f;        // deriv /= stepSize with stepSize = 1 / d (patch_sampler.cc:100,129-130)
+                    }
+                    n0 = nn[0]; n1 = nn[1]; n2 = nn[2]; d0 = dv[0]; d1 = dv[1]; d2 = dv[2];
+                }
             }
+            pw(PW_N + 3 * s) = n0; pw(PW_N + 3 * s + 1) = n1; pw(PW_N + 3 * s + 2) = n2;
+            pw(PW_D + 3 * s) = d0; pw(PW_D + 3 * s + 1) = d1; pw(PW_D + 3 * s + 2) = d2;
+            sn[0] += n0; sn[1] += n1; sn[2] += n2;
         }
+        if (gany(oob)) return 0u;
         return dok ? 3u : 1u;
-    }
-
-    // getFastNCC on given colour samples (patch_sampler.cc:143-162)
-    __device__ __forceinline__ float ncc_of(const float (&n)[3]) const
-    {
-        const float inv_n = 1.f / (float)NS;
-        float my0 = n[0], my1 = n[1], my2 = n[2], pad = 0.f;
-        warp_sum4(lane, my0, my1, my2, pad);
-        my0 *= inv_n; my1 *= inv_n; my2 *= inv_n;
-        const float y0 = act ? n[0] - my0 : 0.f, y1 = act ? n[1] - my1 : 0.f, y2 = act ? n[2] - my2 : 0.f;
-        float sqrDevY = y0 * y0 + y1 * y1 + y2 * y2;
-        float devXY = e0 * y0 + e1 * y1 + e2 * y2;
-        warp_sum2(lane, sqrDevY, devXY);
-        const float p = sqrDevX * sqrDevY;              // devXY / sqrt(p), -1 when sqrt(p) is not > 0
-        return p > 0.f ? devXY * rsqrt_fast(p) : -1.f;
     }
 
     // One pass at the current state (see the header comment).
@@ -360,35 +397,86 @@ struct Patch {
         bool cs_active = cs_pending && st->use_color_scale;
         if (!candidates) { p_col_ok = p_der_ok = 0u; }
         const int count = candidates ? job->n_global : nsel;
+#pragma unroll 1
         for (int k = 0; k < count; ++k) {
             int slot = k;
             if (candidates) { if (!((avail >> k) & 1u)) continue; }
-            else slot = __shfl_sync(FULL, sel_l, k);
-            float n[3], d[3];
-            const unsigned r = sample(&views[job->gview[slot]], n, d);
-            if (candidates) {
-                const float v = (r & 1u) ? ncc_of(n) : -1.f;
-                if (v < st->min_ncc) avail &= ~(1u << k);
-                else if (lane == k) cand_ncc_l = v;
-                continue;
+            else slot = gbcast(sel_l, k);
+            float sn[3];
+            const unsigned r = sample(&views[job->gview[slot]], sn);
+            const bool need_ncc = (candidates || want_ncc) && (r & 1u);
+            float c0 = gbcast(cs0_l, k), c1 = gbcast(cs1_l, k), c2 = gbcast(cs2_l, k);
+            const bool cs_now = !candidates && cs_active && (r & 1u);
+            if (!candidates) {
+                if (r & 1u) p_col_ok |= 1u << k;
+                if (r & 2u) p_der_ok |= 1u << k;
+                // computeColorScale: a failed view ends the whole update (`return`, not `continue`, patch_optimization.cc:92-93)
+                if (cs_active && !(r & 1u)) cs_active = false;
             }
-            if (r & 1u) p_col_ok |= 1u << k;
-            if (r & 2u) p_der_ok |= 1u << k;
-            if (want_ncc) {
-                const float v = (r & 1u) ? ncc_of(n) : -1.f;
-                if (lane == k) ncc_l = v;
+            float ncc = -1.f;
+            float my0 = 0.f, my1 = 0.f, my2 = 0.f;
+            if (need_ncc) {                               // getFastNCC (patch_sampler.cc:143-162): means first
+                const float inv_n = 1.f / (float)NS;
+                my0 = gsum(sn[0]) * inv_n; my1 = gsum(sn[1]) * inv_n; my2 = gsum(sn[2]) * inv_n;
             }
-            float c0 = __shfl_sync(FULL, cs0_l, k), c1 = __shfl_sync(FULL, cs1_l, k), c2 = __shfl_sync(FULL, cs2_l, k);
-            // computeColorScale for this view (patch_optimization.cc:88-110); a failed view ends the whole
-            // update (`return`, not `continue`, :92-93)
-            if (cs_active) {
-                if (!(r & 1u)) cs_active = false;
-                else {
+            // second sweep over the lane's samples (from shared memory): NCC deviations, colour-scale sums, and the
+            // Gauss-Newton terms; when the colour scale is updated at this state the terms need the NEW scale, so they are
+            // formed in a repetition of the same loop
+#pragma unroll 1
+            for (int rep = 0; rep < 2; ++rep) {
+                const bool do_ncc = rep == 0 && need_ncc;
+                const bool do_cs = rep == 0 && cs_now;
+                const bool do_gn = !candidates && (r & 2u) && (rep == (cs_now ? 1 : 0));
+                if (!(do_ncc || do_cs || do_gn)) continue;
+                float sqrDevY = 0.f, devXY = 0.f;
+                float ab0 = 0.f, ab1 = 0.f, ab2 = 0.f, aa0 = 0.f, aa1 = 0.f, aa2 = 0.f;
+#pragma unroll 1
+                for (int s = 0; s < SLOTS; ++s) {
+                    if (!is_real(s)) continue;
+                    const float n0 = pw(PW_N + 3 * s), n1 = pw(PW_N + 3 * s + 1), n2 = pw(PW_N + 3 * s + 2);
+                    const float m0 = pw(PW_M + 3 * s), m1 = pw(PW_M + 3 * s + 1), m2 = pw(PW_M + 3 * s + 2);
+                    if (do_ncc) {
+                        const float y0 = n0 - my0, y1 = n1 - my1, y2 = n2 - my2;
+                        sqrDevY += y0 * y0 + y1 * y1 + y2 * y2;
+                        devXY += (m0 - mx0) * y0 + (m1 - mx1) * y1 + (m2 - mx2) * y2;
+                    }
+                    if (do_cs) {                          // patch_optimization.cc:95-101
+                        ab0 += (m0 - n0 * c0) * n0; ab1 += (m1 - n1 * c1) * n1; ab2 += (m2 - n2 * c2) * n2;
+                        aa0 += n0 * n0; aa1 += n1 * n1; aa2 += n2 * n2;
+                    }
+                    if (do_gn) {
+                        // Gauss-Newton terms (patch_optimization.cc:283-288 / :324-343); only meaningful when every view's
+                        // derivative path succeeded, which the caller checks through p_der_ok
+                        const float g0 = c0 * pw(PW_D + 3 * s), g1 = c1 * pw(PW_D + 3 * s + 1), g2 = c2 * pw(PW_D + 3 * s + 2);
+                        const float r0 = m0 - c0 * n0, r1 = m1 - c1 * n1, r2 = m2 - c2 * n2;
+                        num += g0 * r0 + g1 * r1 + g2 * r2;
+                        den += g0 * g0 + g1 * g1 + g2 * g2;
+                        if (want_normal) {
+                            const int ks = sample_index(s);
+                            const float fi = (float)(ks % 5 - 2), fj = (float)(ks / 5 - 2);
+                            const float gg[3] = {g0, g1, g2};
+                            const float rr[3] = {r0, r1, r2};
+#pragma unroll
+                            for (int ch = 0; ch < 3; ++ch) {
+                                const float a0 = gg[ch];
+                                const float a1 = fi * a0;      // (ii * cs) * deriv == ii * (cs * deriv) exactly for ii in {-2..2}
+                                const float a2 = fj * a0;
+                                A0 += a0 * a0; A1 += a0 * a1; A2 += a0 * a2;
+                                A3 += a1 * a1; A4 += a1 * a2; A5 += a2 * a2;
+                                B0 += a0 * rr[ch]; B1 += a1 * rr[ch]; B2 += a2 * rr[ch];
+                            }
+                        }
+                    }
+                }
+                if (do_ncc) {
+                    sqrDevY = gsum(sqrDevY); devXY = gsum(devXY);
+                    const float p = sqrDevX * sqrDevY;          // devXY / sqrt(p), -1 when sqrt(p) is not > 0
+                    ncc = p > 0.f ? devXY * rsqrt_fast(p) : -1.f;
+                }
+                if (do_cs) {
                     float cc[3] = {c0, c1, c2};
-                    float ab[3] = {(m0 - n[0] * c0) * n[0], (m1 - n[1] * c1) * n[1], (m2 - n[2] * c2) * n[2]};
-                    float aa[3] = {n[0] * n[0], n[1] * n[1], n[2] * n[2]};
-                    warp_sum4(lane, ab[0], ab[1], ab[2], aa[0]);
-                    warp_sum2(lane, aa[1], aa[2]);
+                    const float ab[3] = {gsum(ab0), gsum(ab1), gsum(ab2)};
+                    const float aa[3] = {gsum(aa0), gsum(aa1), gsum(aa2)};
 #pragma unroll
                     for (int ch = 0; ch < 3; ++ch) {
                         if ((double)fabsf(aa[ch]) > 1e-6) {
@@ -398,44 +486,30 @@ struct Patch {
                             opti = false;
                     }
                     c0 = cc[0]; c1 = cc[1]; c2 = cc[2];
-                    if (lane == k) { cs0_l = c0; cs1_l = c1; cs2_l = c2; }
+                    if (gl == k) { cs0_l = c0; cs1_l = c1; cs2_l = c2; }
                 }
             }
-            // Gauss-Newton terms (patch_optimization.cc:283-288 / :324-343); only meaningful when every view's
-            // derivative path succeeded, which the caller checks through p_der_ok
-            if ((r & 2u) && act) {
-                const float g0 = c0 * d[0], g1 = c1 * d[1], g2 = c2 * d[2];
-                const float r0 = m0 - c0 * n[0], r1 = m1 - c1 * n[1], r2 = m2 - c2 * n[2];
-                num += g0 * r0 + g1 * r1 + g2 * r2;
-                den += g0 * g0 + g1 * g1 + g2 * g2;
-                if (want_normal) {
-                    const float gg[3] = {g0, g1, g2};
-                    const float rr[3] = {r0, r1, r2};
-#pragma unroll
-                    for (int ch = 0; ch < 3; ++ch) {
-                        const float a0 = gg[ch];
-                        const float a1 = fi * a0;      // (ii * cs) * deriv == ii * (cs * deriv) exactly for ii in {-2..2}
-                        const float a2 = fj * a0;
-                        A0 += a0 * a0; A1 += a0 * a1; A2 += a0 * a2;
-                        A3 += a1 * a1; A4 += a1 * a2; A5 += a2 * a2;
-                        B0 += a0 * rr[ch]; B1 += a1 * rr[ch]; B2 += a2 * rr[ch];
-                    }
+            if (candidates) {
+                if (ncc < st->min_ncc) avail &= ~(1u << k);
+                else if (gl == (k & (GROUP - 1))) {
+                    const int j = k >> 3;
+                    if (j == 0) cand0 = ncc; else if (j == 1) cand1 = ncc; else if (j == 2) cand2 = ncc; else cand3 = ncc;
                 }
-            }
+            } else if (want_ncc && gl == k)
+                ncc_l = ncc;
         }
         if (candidates) return;
-        warp_sum2(lane, num, den);
-        p_num = num; p_den = den;
+        p_num = gsum(num); p_den = gsum(den);
         p_has_normal = want_normal;
         p_has_ncc = want_ncc;
         if (want_normal) {
-            // solve here so that the nine fp64 sums die with the pass (matrix_tools.h:392-398,460-475)
-            // the lane's <= 12 products (3 channels x <= 4 views) are summed in fp32, the 25 lanes in fp64; the reference sums
+            // solve here so that the nine fp64 sums die with the pass (matrix_tools.h:392-398,460-475).  The lane's <= 48
+            // products (3 channels x <= 4 samples x <= 4 views) are summed in fp32, the 8 lanes in fp64; the reference sums
             // all 300 fp32 products in fp64 (patch_optimization.cc:336-342).  The difference (~1e-7 relative on ATA) is far
             // below what the Gauss-Newton fixed point resolves; measured in tests/test_gpu_parity.py.
-            const double D0 = warp_sum((double)A0), D1 = warp_sum((double)A1), D2 = warp_sum((double)A2), D3 = warp_sum((double)A3);
-            const double D4 = warp_sum((double)A4), D5 = warp_sum((double)A5);
-            const double E0 = warp_sum((double)B0), E1 = warp_sum((double)B1), E2 = warp_sum((double)B2);
+            const double D0 = gsum((double)A0), D1 = gsum((double)A1), D2 = gsum((double)A2), D3 = gsum((double)A3);
+            const double D4 = gsum((double)A4), D5 = gsum((double)A5);
+            const double E0 = gsum((double)B0), E1 = gsum((double)B1), E2 = gsum((double)B2);
             const double m[9] = {D0, D1, D2, D1, D3, D4, D2, D4, D5};
             const double det = m[0] * m[4] * m[8] + m[1] * m[5] * m[6] + m[2] * m[3] * m[7]
                              - m[2] * m[4] * m[6] - m[1] * m[3] * m[8] - m[0] * m[5] * m[7];
@@ -491,25 +565,25 @@ struct Patch {
         int src = 0, cnt = 0;
         for (int k = 0; k < MAX_LOCAL; ++k) {
             const bool kk = k < nsel && !((mask >> k) & 1u);
-            if (kk) { if (cnt == lane) src = k; ++cnt; }
+            if (kk) { if (cnt == gl) src = k; ++cnt; }
         }
-        const int s = __shfl_sync(FULL, sel_l, src);
-        const float a = __shfl_sync(FULL, cs0_l, src), b = __shfl_sync(FULL, cs1_l, src), c = __shfl_sync(FULL, cs2_l, src);
-        const float v = __shfl_sync(FULL, ncc_l, src);
+        const int s = gbcast(sel_l, src);
+        const float a = gbcast(cs0_l, src), b = gbcast(cs1_l, src), c = gbcast(cs2_l, src);
+        const float v = gbcast(ncc_l, src);
         nsel = cnt;
-        if (lane < cnt) { sel_l = s; cs0_l = a; cs1_l = b; cs2_l = c; ncc_l = v; }
+        if (gl < cnt) { sel_l = s; cs0_l = a; cs1_l = b; cs2_l = c; ncc_l = v; }
         else { sel_l = 0xFF; }
     }
     __device__ __forceinline__ void sel_insert(int slot, float cs_init)
     {
         // position = number of selected slots smaller than `slot`
-        const unsigned smaller = __ballot_sync(FULL, lane < nsel && sel_l < slot);
+        const unsigned smaller = gballot(gl < nsel && sel_l < slot);
         const int pos = __popc(smaller);
-        const int s_up = __shfl_up_sync(FULL, sel_l, 1);
-        const float a_up = __shfl_up_sync(FULL, cs0_l, 1), b_up = __shfl_up_sync(FULL, cs1_l, 1), c_up = __shfl_up_sync(FULL, cs2_l, 1);
-        const float v_up = __shfl_up_sync(FULL, ncc_l, 1);
-        if (lane > pos && lane <= nsel) { sel_l = s_up; cs0_l = a_up; cs1_l = b_up; cs2_l = c_up; ncc_l = v_up; }
-        if (lane == pos) { sel_l = slot; cs0_l = cs1_l = cs2_l = cs_init; ncc_l = 0.f; }
+        const int s_up = __shfl_up_sync(gmask, sel_l, 1, GROUP);
+        const float a_up = __shfl_up_sync(gmask, cs0_l, 1, GROUP), b_up = __shfl_up_sync(gmask, cs1_l, 1, GROUP), c_up = __shfl_up_sync(gmask, cs2_l, 1, GROUP);
+        const float v_up = __shfl_up_sync(gmask, ncc_l, 1, GROUP);
+        if (gl > pos && gl <= nsel) { sel_l = s_up; cs0_l = a_up; cs1_l = b_up; cs2_l = c_up; ncc_l = v_up; }
+        if (gl == pos) { sel_l = slot; cs0_l = cs1_l = cs2_l = cs_init; ncc_l = 0.f; }
         ++nsel;
     }
 
@@ -524,8 +598,23 @@ struct Patch {
     static __device__ __forceinline__ float clamp1(float v) { return v < -1.f ? -1.f : (v > 1.f ? 1.f : v); }
     static __device__ __forceinline__ float deg_acos(float dp) { return acosf(dp) * 180.f / 3.141592653589793f; }
 
+    // viewDir / epipolar plane / footprint of global slot `slot` at patchPoints[12] (local_view_selection.cc:93-131)
+    __device__ __forceinline__ void cand_geometry(int slot, float rdx, float rdy, float rdz,
+                                                  float& vdx, float& vdy, float& vdz, float& epx, float& epy, float& epz, float& nfp) const
+    {
+        const ViewParams* V = &views[job->gview[slot]];
+        vdx = cpx - __ldg(&V->campos[0]); vdy = cpy - __ldg(&V->campos[1]); vdz = cpz - __ldg(&V->campos[2]);
+        const float nn = sqrtf(vdx * vdx + vdy * vdy + vdz * vdz);
+        vdx /= nn; vdy /= nn; vdz /= nn;
+        epx = vdy * rdz - vdz * rdy; epy = vdz * rdx - vdx * rdz; epz = vdx * rdy - vdy * rdx;
+        const float en = sqrtf(epx * epx + epy * epy + epz * epz);
+        epx /= en; epy /= en; epz /= en;
+        const float z = __ldg(&V->w2c[8]) * cpx + __ldg(&V->w2c[9]) * cpy + __ldg(&V->w2c[10]) * cpz + __ldg(&V->w2c[11]);
+        nfp = z * __ldg(&V->inv_ax0);
+    }
+
     // Second half of LocalViewSelection::performVS (local_view_selection.cc:86-147): greedy selection among the
-    // candidates that survived the NCC test of pass(candidates = true); lane i evaluates candidate slot i.
+    // candidates that survived the NCC test of pass(candidates = true); lane gl evaluates candidate slots gl + 8 j.
     __device__ __forceinline__ void lvs_greedy()
     {
         const unsigned N = st->nr_recon_neighbors;
@@ -536,37 +625,30 @@ struct Patch {
             rdx /= nn; rdy /= nn; rdz /= nn;
         }
         const int G = job->n_global;
-        // per-lane candidate geometry (viewDir, epipolarPlane, footprint)
-        float vdx = 0.f, vdy = 0.f, vdz = 1.f, epx = 0.f, epy = 0.f, epz = 1.f, nfp = 1.f;
-        if (lane < G) {
-            const ViewParams* V = &views[job->gview[lane]];
-            vdx = cpx - __ldg(&V->campos[0]); vdy = cpy - __ldg(&V->campos[1]); vdz = cpz - __ldg(&V->campos[2]);
-            const float nn = sqrtf(vdx * vdx + vdy * vdy + vdz * vdz);
-            vdx /= nn; vdy /= nn; vdz /= nn;
-            epx = vdy * rdz - vdz * rdy; epy = vdz * rdx - vdx * rdz; epz = vdx * rdy - vdy * rdx;
-            const float en = sqrtf(epx * epx + epy * epy + epz * epz);
-            epx /= en; epy /= en; epz /= en;
-            const float z = __ldg(&V->w2c[8]) * cpx + __ldg(&V->w2c[9]) * cpy + __ldg(&V->w2c[10]) * cpz + __ldg(&V->w2c[11]);
-            nfp = z * __ldg(&V->inv_ax0);
-        }
         bool found = true;
         while ((unsigned)nsel < N && found) {
             found = false;
-            const bool mine = lane < G && ((avail >> lane) & 1u);
-            float score = -1.f;
-            if (mine) {
-                score = cand_ncc_l;
+            float best_score = -1.f;
+            int best_slot = 0x7FFFFFFF;
+            // the already selected views, ascending (std::set iteration order); read before the lanes diverge
+            const int ss0 = gbcast(sel_l, 0), ss1 = gbcast(sel_l, 1), ss2 = gbcast(sel_l, 2), ss3 = gbcast(sel_l, 3);
+#pragma unroll 1
+            for (int j = 0; j < MAX_GLOBAL / GROUP; ++j) {
+                const int c = gl + GROUP * j;
+                if (!(c < G && ((avail >> c) & 1u))) continue;
+                float vdx, vdy, vdz, epx, epy, epz, nfp;
+                cand_geometry(c, rdx, rdy, rdz, vdx, vdy, vdz, epx, epy, epz, nfp);
+                float score = j == 0 ? cand0 : (j == 1 ? cand1 : (j == 2 ? cand2 : cand3));
                 if (mfp / nfp < 0.5f) score *= 0.01f;
                 float dp = clamp1(rdx * vdx + rdy * vdy + rdz * vdz);
                 score *= plx_weight(deg_acos(dp));
-            }
-            // parallax / epipolar terms against every already selected view (geometry broadcast from its lane)
-            for (int k = 0; k < nsel; ++k) {
-                const int s = __shfl_sync(FULL, sel_l, k);
-                const float sx = __shfl_sync(FULL, vdx, s), sy = __shfl_sync(FULL, vdy, s), sz = __shfl_sync(FULL, vdz, s);
-                const float ex = __shfl_sync(FULL, epx, s), ey = __shfl_sync(FULL, epy, s), ez = __shfl_sync(FULL, epz, s);
-                if (mine) {
-                    float dp = clamp1(sx * vdx + sy * vdy + sz * vdz);
+                // parallax / epipolar terms against every already selected view
+#pragma unroll 1
+                for (int k = 0; k < nsel; ++k) {
+                    const int s = k == 0 ? ss0 : (k == 1 ? ss1 : (k == 2 ? ss2 : ss3));
+                    float sx, sy, sz, ex, ey, ez, sfp;
+                    cand_geometry(s, rdx, rdy, rdz, sx, sy, sz, ex, ey, ez, sfp);
+                    dp = clamp1(sx * vdx + sy * vdy + sz * vdz);
                     score *= plx_weight(deg_acos(dp));
                     dp = clamp1(epx * ex + epy * ey + epz * ez);
                     float angle = fabsf(deg_acos(dp));
@@ -574,12 +656,15 @@ struct Patch {
                     angle = fmaxf(angle, 1.f);
                     if (angle < st->min_parallax) score *= angle / st->min_parallax;
                 }
+                // strict '>' in ascending slot order: the lowest slot wins ties (local_view_selection.cc:133-137); NaN never wins
+                if (score > 0.f && score > best_score) { best_score = score; best_slot = c; }
             }
-            const bool cand = mine && (score > 0.f);       // NaN compares false, like `score > maxScore`
-            const float best = warp_max(cand ? score : -1.f);
-            const unsigned winners = __ballot_sync(FULL, cand && score == best);
-            if (best > 0.f && winners) {
-                const int w = __ffs(winners) - 1;           // strict '>' in index order: lowest index wins ties
+            const float best = gmax(best_score);
+            const bool mine = best_score > 0.f && best_score == best;
+            int w = mine ? best_slot : 0x7FFFFFFF;
+#pragma unroll
+            for (int o = GROUP / 2; o > 0; o >>= 1) w = min(w, __shfl_xor_sync(gmask, w, o));
+            if (best > 0.f && w != 0x7FFFFFFF) {
                 found = true;
                 sel_insert(w, cs_init);
                 avail &= ~(1u << w);
@@ -589,92 +674,91 @@ struct Patch {
     }
 
     // PatchOptimization ctor (patch_optimization.cc:21-78) incl. LocalViewSelection ctor (local_view_selection.cc:19-54),
-    // up to the point where the first sample sets are needed.
-    __device__ __forceinline__ void init(const PatchIn& in)
+    // up to the point where the first sample sets are needed; sets the first stage of the state machine.
+    __device__ __forceinline__ void begin(const JobParams* j, const PatchIn& in)
     {
+        job = j;
         rv = &views[job->ref_view];
+        x0 = in.x; y0 = in.y;
         depth = in.depth; dzI = in.dzI; dzJ = in.dzJ;
         iter = 0; opti = true; converged = false; lvs_ok = false;
         nsel = 0; avail = 0u;
-        sel_l = 0xFF; cs0_l = cs1_l = cs2_l = 0.f; ncc_l = 0.f; cand_ncc_l = 0.f;
+        sel_l = 0xFF; cs0_l = cs1_l = cs2_l = 0.f; ncc_l = 0.f; cand0 = cand1 = cand2 = cand3 = 0.f;
         p_col_ok = p_der_ok = 0u; p_num = p_den = 0.f; p_has_normal = p_has_ncc = false;
         nX0 = nX1 = nX2 = 0.f; n_singular = true;
+        viewRemoved = was_normal = normal = false; old = 0.f;
+        stage = DONE;
         init_sampler(in.x, in.y);
         // propagated ids arrive ascending, 0xFF padded
-        if (lane < MAX_LOCAL) sel_l = (in.slots >> (8 * lane)) & 0xFF;
-        nsel = __popc(__ballot_sync(FULL, lane < MAX_LOCAL && sel_l != 0xFF));
+        if (gl < MAX_LOCAL) sel_l = (in.slots >> (8 * gl)) & 0xFF;
+        nsel = __popc(gballot(gl < MAX_LOCAL && sel_l != 0xFF));
         if (!ref_ok) { opti = false; return; }
         const unsigned N = st->nr_recon_neighbors;
         if ((unsigned)nsel == N) lvs_ok = true;
         else if ((unsigned)nsel > N) { nsel = 0; sel_l = 0xFF; }
         avail = job->n_global >= 32 ? FULL : ((1u << job->n_global) - 1u);
         unsigned m = 0u;
-        for (int k = 0; k < nsel; ++k) m |= 1u << __shfl_sync(FULL, sel_l, k);
+        for (int k = 0; k < nsel; ++k) m |= 1u << gbcast(sel_l, k);
         avail &= ~m;
         cs0_l = cs1_l = cs2_l = 1.f / mm;
+        stage = lvs_ok ? CTOR : LVS_CTOR;
     }
 
     // The rest of the ctor (performVS, computeColorScale) and PatchOptimization::doAutoOptimization
-    // (patch_optimization.cc:66-77,170-242) as a state machine around the single pass() call site.
-    __device__ __forceinline__ void auto_optimize()
+    // (patch_optimization.cc:66-77,170-242) as a state machine around the single pass() call site: one call = one pass
+    // plus everything up to the next one.  Returns true when the optimisation is over.
+    __device__ __forceinline__ bool step()
     {
-        if (!opti) return;
-        enum Stage { LVS_CTOR, CTOR, FIRST, PRE, POST, LVS_REPL, REPL };
-        int stage = lvs_ok ? CTOR : LVS_CTOR;
-        bool viewRemoved = false, was_normal = false, normal = false;
-        float old = 0.f;
-        for (;;) {
-            // arguments of the one pass() call, by stage
-            const bool a_cand = (stage == LVS_CTOR) | (stage == LVS_REPL);
-            const bool a_cs = (stage == CTOR) | (stage == REPL) | ((stage == POST) & was_normal);   // computeColorScale of :77, :230, :198
-            const bool a_ncc = (stage == PRE) | (stage == POST) | (stage == REPL) | ((stage == FIRST) & (iter == 4));
-            const bool a_normal = (stage == REPL) | ((stage == FIRST) & (iter == 4)) | ((stage == PRE) & normal) |
-                                  ((stage == POST) & ((iter + 1) % 5 == 4));
-            pass(a_cand, a_cs, a_ncc, a_normal);
-            if (stage == LVS_CTOR || stage == LVS_REPL) {
-                lvs_greedy();
-                if (!lvs_ok) { if (stage == LVS_CTOR) opti = false; return; }
-                stage = (stage == LVS_CTOR) ? CTOR : REPL;
-                continue;
-            }
-            if (!opti) return;            // a colour scale failed: every caller of computeColorScale gives up here
-            if (stage == POST) {
-                const float df = fabsf(ncc_l - old);
-                const bool mine = lane < nsel;
-                const bool conv = !__any_sync(FULL, mine && df > st->min_refine_diff);
-                const unsigned tbr = __ballot_sync(FULL, mine && (ncc_l < st->accept_ncc || (iter == 14 && df > st->min_refine_diff)));
-                if (tbr) {
-                    viewRemoved = true;
-                    sel_erase_mask(tbr);          // LocalViewSelection::replaceViews (local_view_selection.cc:150-160)
-                    lvs_ok = false;
-                    stage = LVS_REPL;
-                    continue;
-                }
-                if (conv) { converged = true; return; }
-                ++iter;
-            } else if (stage == REPL) {
-                ++iter;
-            }
-            // first four iterations only refine depth (:177-180)
-            bool need_pass = false;
-            while (iter < 4 && opti) {
-                const bool moved = depth_step();
-                ++iter;
-                if (moved && opti) { stage = FIRST; need_pass = true; break; }
-            }
-            if (need_pass) continue;
-            if (!opti) return;
-            // head of the main loop (:184-203)
-            if (!((unsigned)iter < st->max_iterations && lvs_ok)) return;
-            normal = (iter % 5 == 4) || viewRemoved;
-            if (!p_has_ncc || (normal && !p_has_normal)) { stage = PRE; continue; }   // only after a depth step with denom <= 0
-            old = ncc_l;                  // oldNCC (:190-193)
-            opti = false;
-            if (normal) { normal_step(); viewRemoved = false; was_normal = true; }
-            else { depth_step(); was_normal = false; }
-            if (!opti) return;
-            stage = POST;
+        if (stage == DONE) return true;
+        // arguments of the one pass() call, by stage
+        const bool a_cand = (stage == LVS_CTOR) | (stage == LVS_REPL);
+        const bool a_cs = (stage == CTOR) | (stage == REPL) | ((stage == POST) & was_normal);   // computeColorScale of :77, :230, :198
+        const bool a_ncc = (stage == PRE) | (stage == POST) | (stage == REPL) | ((stage == FIRST) & (iter == 4));
+        const bool a_normal = (stage == REPL) | ((stage == FIRST) & (iter == 4)) | ((stage == PRE) & normal) |
+                              ((stage == POST) & ((iter + 1) % 5 == 4));
+        pass(a_cand, a_cs, a_ncc, a_normal);
+        if (stage == LVS_CTOR || stage == LVS_REPL) {
+            lvs_greedy();
+            if (!lvs_ok) { if (stage == LVS_CTOR) opti = false; stage = DONE; return true; }
+            stage = (stage == LVS_CTOR) ? CTOR : REPL;
+            return false;
         }
+        if (!opti) { stage = DONE; return true; }        // a colour scale failed: every caller of computeColorScale gives up here
+        if (stage == POST) {
+            const float df = fabsf(ncc_l - old);
+            const bool mine = gl < nsel;
+            const bool conv = !gany(mine && df > st->min_refine_diff);
+            const unsigned tbr = gballot(mine && (ncc_l < st->accept_ncc || (iter == 14 && df > st->min_refine_diff)));
+            if (tbr) {
+                viewRemoved = true;
+                sel_erase_mask(tbr);          // LocalViewSelection::replaceViews (local_view_selection.cc:150-160)
+                lvs_ok = false;
+                stage = LVS_REPL;
+                return false;
+            }
+            if (conv) { converged = true; stage = DONE; return true; }
+            ++iter;
+        } else if (stage == REPL) {
+            ++iter;
+        }
+        // first four iterations only refine depth (:177-180)
+        while (iter < 4 && opti) {
+            const bool moved = depth_step();
+            ++iter;
+            if (moved && opti) { stage = FIRST; return false; }
+        }
+        if (!opti) { stage = DONE; return true; }
+        // head of the main loop (:184-203)
+        if (!((unsigned)iter < st->max_iterations && lvs_ok)) { stage = DONE; return true; }
+        normal = (iter % 5 == 4) || viewRemoved;
+        if (!p_has_ncc || (normal && !p_has_normal)) { stage = PRE; return false; }   // only after a depth step with denom <= 0
+        old = ncc_l;                  // oldNCC (:190-193)
+        opti = false;
+        if (normal) { normal_step(); viewRemoved = false; was_normal = true; }
+        else { depth_step(); was_normal = false; }
+        if (!opti) { stage = DONE; return true; }
+        stage = POST;
+        return false;
     }
 
     // PatchOptimization::computeConfidence (patch_optimization.cc:114-142) + getPatchNormal (patch_sampler.cc:243-256)
@@ -686,7 +770,7 @@ struct Patch {
         unsigned s = 0u;
 #pragma unroll
         for (int k = 0; k < MAX_LOCAL; ++k) {
-            const int v = __shfl_sync(FULL, sel_l, k);
+            const int v = gbcast(sel_l, k);
             s |= (unsigned)((k < nsel) ? (v & 0xFF) : 0xFF) << (8 * k);
         }
         out.slots = s;
@@ -694,15 +778,30 @@ struct Patch {
         if (!converged) return;
         // mean NCC of the final state (the NCCs of the last pass)
         float mean = 0.f;
-        for (int k = 0; k < nsel; ++k) mean += __shfl_sync(FULL, ncc_l, k);
+        for (int k = 0; k < nsel; ++k) mean += gbcast(ncc_l, k);
         mean /= (float)nsel;
         const float score = (mean - st->accept_ncc) / (1.f - st->accept_ncc);
-        const float ax_ = __shfl_sync(FULL, px, CENTER + 2) - __shfl_sync(FULL, px, CENTER - 2);
-        const float ay_ = __shfl_sync(FULL, py, CENTER + 2) - __shfl_sync(FULL, py, CENTER - 2);
-        const float az_ = __shfl_sync(FULL, pz, CENTER + 2) - __shfl_sync(FULL, pz, CENTER - 2);
-        const float bx_ = __shfl_sync(FULL, px, 2) - __shfl_sync(FULL, px, NS - 1 - 2);
-        const float by_ = __shfl_sync(FULL, py, 2) - __shfl_sync(FULL, py, NS - 1 - 2);
-        const float bz_ = __shfl_sync(FULL, pz, 2) - __shfl_sync(FULL, pz, NS - 1 - 2);
+        // patchPoints[14] - patchPoints[10] and patchPoints[2] - patchPoints[22]: samples 10, 14 live in slot 2 (lanes 2, 6),
+        // sample 2 in slot 1 (lane 2), sample 22 in slot 3 (lane 6)
+        float q1x, q1y, q1z, q2x, q2y, q2z, q3x, q3y, q3z;
+        {
+            const float c0x = __ldg(&rv->campos[0]), c0y = __ldg(&rv->campos[1]), c0z = __ldg(&rv->campos[2]);
+            int k = sample_index(1);
+            float t = depth + (float)(k % 5 - 2) * dzI + (float)(k / 5 - 2) * dzJ;
+            q1x = c0x + t * pw(PW_RAY + 3); q1y = c0y + t * pw(PW_RAY + 4); q1z = c0z + t * pw(PW_RAY + 5);
+            k = sample_index(2);
+            t = depth + (float)(k % 5 - 2) * dzI + (float)(k / 5 - 2) * dzJ;
+            q2x = c0x + t * pw(PW_RAY + 6); q2y = c0y + t * pw(PW_RAY + 7); q2z = c0z + t * pw(PW_RAY + 8);
+            k = sample_index(3);
+            t = depth + (float)(k % 5 - 2) * dzI + (float)(k / 5 - 2) * dzJ;
+            q3x = c0x + t * pw(PW_RAY + 9); q3y = c0y + t * pw(PW_RAY + 10); q3z = c0z + t * pw(PW_RAY + 11);
+        }
+        const float ax_ = gbcast(q2x, 6) - gbcast(q2x, 2);
+        const float ay_ = gbcast(q2y, 6) - gbcast(q2y, 2);
+        const float az_ = gbcast(q2z, 6) - gbcast(q2z, 2);
+        const float bx_ = gbcast(q1x, 2) - gbcast(q3x, 6);
+        const float by_ = gbcast(q1y, 2) - gbcast(q3y, 6);
+        const float bz_ = gbcast(q1z, 2) - gbcast(q3z, 6);
         float nx = ay_ * bz_ - az_ * by_, ny = az_ * bx_ - ax_ * bz_, nz = ax_ * by_ - ay_ * bx_;
         const float nn = sqrtf(nx * nx + ny * ny + nz * nz);
         nx /= nn; ny /= nn; nz /= nn;
@@ -712,16 +811,20 @@ struct Patch {
     }
 };
 
-// One PatchOptimization executed by the calling warp.  Returns the number of fused sample sets drawn.
-__device__ __forceinline__ unsigned optimize_patch(const DevSettings* st, const JobParams* job, const ViewParams* views,
-                                                   const float* lut, int lane, const PatchIn& in, PatchOut& out)
+// Binds a thread to its group and its shared-memory columns.  lut_rep: LUT_REP-fold replicated table
+// (lut_rep[v * LUT_REP + r] = srgb2lin[v]), priv_base: PRIV_WORDS * TPB floats of the block, tid: thread index in the block.
+template <int TPB>
+__device__ __forceinline__ void bind_thread(Patch<TPB>& p, const DevSettings* st, const ViewParams* views,
+                                            const float* lut_rep, float* priv_base, int tid)
 {
-    Patch p;
-    p.st = st; p.job = job; p.views = views; p.lut = lut; p.lane = lane;
-    p.init(in);
-    p.auto_optimize();
-    p.finish(out);
-    return p.n_sets;
+    const int lane = tid & 31;
+    p.st = st; p.views = views;
+    p.lutw = lut_rep + (lane & (LUT_REP - 1));
+    p.priv = priv_base + tid;
+    p.gl = lane & (GROUP - 1);
+    p.gmask = ((1u << GROUP) - 1u) << (lane & ~(GROUP - 1));
+    p.stage = Patch<TPB>::DONE;
+    p.n_sets = 0u;
 }
 
 } // namespace b200mvs

@@ -14,6 +14,7 @@ thread_local int t_sense_sub = 0;
 
 #include "../../mve_b200/csrc/patch_opt.cuh"
 
+#include <atomic>
 #include <thread>
 #include <vector>
 
@@ -28,6 +29,7 @@ struct EmuView {
     float ax[MAX_LEVELS], ay[MAX_LEVELS], cx[MAX_LEVELS], cy[MAX_LEVELS];
     int w[MAX_LEVELS], h[MAX_LEVELS], pitch[MAX_LEVELS];
     const uchar4* img[MAX_LEVELS];
+    const uint4* quad[MAX_LEVELS];
 };
 
 struct EmuPatchIn { int x, y; float depth, dzI, dzJ; unsigned slots; };
@@ -56,7 +58,7 @@ int emu_optimize_patches(const EmuView* views, int n_views, int ref_view, int W,
         for (int l = 0; l < views[v].nlevels; ++l) {
             LevelParams& L = vp[v].lv[l];
             L.ax = views[v].ax[l]; L.ay = views[v].ay[l]; L.cx = views[v].cx[l]; L.cy = views[v].cy[l];
-            L.w = views[v].w[l]; L.h = views[v].h[l]; L.pitch = views[v].pitch[l]; L.img = views[v].img[l];
+            L.w = views[v].w[l]; L.h = views[v].h[l]; L.pitch = views[v].pitch[l]; L.img = views[v].img[l]; L.quad = views[v].quad[l];
         }
     }
     DevSettings st;
@@ -71,8 +73,15 @@ int emu_optimize_patches(const EmuView* views, int n_views, int ref_view, int W,
     job.ref_img = views[ref_view].img[st.scale];
     job.ref_pitch = views[ref_view].pitch[st.scale];
 
+    /* one warp = four 8-lane groups; each group takes patches through a ticket counter exactly like the kernels'
+     * optimise_entries() (mve_b200/csrc/b200mvs.cu); "shared memory" = the replicated table + one column per lane */
     simt_emu::Warp warp;
     for (int g = 0; g < 4; ++g) warp.sub8[g].bar.n = 8;
+    std::vector<float> lut_rep(256 * LUT_REP);
+    for (int i = 0; i < 256 * LUT_REP; ++i) lut_rep[i] = lut[i / LUT_REP];
+    constexpr int TPB = 32;
+    std::vector<float> priv(PRIV_WORDS * TPB, 0.f);
+    std::atomic<int> ticket(0);
     std::vector<std::thread> lanes;
     for (int lane = 0; lane < 32; ++lane) {
         lanes.emplace_back([&, lane]() {
@@ -80,15 +89,33 @@ int emu_optimize_patches(const EmuView* views, int n_views, int ref_view, int W,
             simt_emu::t_lane = lane;
             simt_emu::t_sense_full = 0;
             simt_emu::t_sense_sub = 0;
-            for (int i = 0; i < n; ++i) {
-                PatchIn pi;
-                pi.x = in[i].x; pi.y = in[i].y; pi.depth = in[i].depth; pi.dzI = in[i].dzI; pi.dzJ = in[i].dzJ; pi.slots = in[i].slots;
-                PatchOut po;
-                const unsigned sets = optimize_patch(&st, &job, vp.data(), lut, lane, pi, po);
-                if (lane == 0) {
-                    out[i].conf = po.conf; out[i].depth = po.depth; out[i].dzI = po.dzI; out[i].dzJ = po.dzJ;
-                    out[i].nx = po.nx; out[i].ny = po.ny; out[i].nz = po.nz; out[i].slots = po.slots;
-                    out[i].iterations = po.iterations; out[i].flags = po.flags; out[i].sets = sets;
+            Patch<TPB> p;
+            bind_thread(p, &st, vp.data(), lut_rep.data(), priv.data(), lane);
+            bool have = false;
+            int idx = 0;
+            unsigned sets_before = 0;
+            for (;;) {
+                if (!have) {
+                    int w = 0;
+                    if (p.gl == 0) w = ticket.fetch_add(1);
+                    w = p.gbcast(w, 0);
+                    if (w >= n) break;
+                    idx = w;
+                    PatchIn pi;
+                    pi.x = in[w].x; pi.y = in[w].y; pi.depth = in[w].depth; pi.dzI = in[w].dzI; pi.dzJ = in[w].dzJ; pi.slots = in[w].slots;
+                    sets_before = p.n_sets;
+                    p.begin(&job, pi);
+                    have = true;
+                }
+                if (p.step()) {
+                    PatchOut po;
+                    p.finish(po);
+                    if (p.gl == 0) {
+                        out[idx].conf = po.conf; out[idx].depth = po.depth; out[idx].dzI = po.dzI; out[idx].dzJ = po.dzJ;
+                        out[idx].nx = po.nx; out[idx].ny = po.ny; out[idx].nz = po.nz; out[idx].slots = po.slots;
+                        out[idx].iterations = po.iterations; out[idx].flags = po.flags; out[idx].sets = p.n_sets - sets_before;
+                    }
+                    have = false;
                 }
             }
         });

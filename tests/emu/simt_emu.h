@@ -30,6 +30,8 @@
 struct uchar4 { unsigned char x, y, z, w; };
 struct float4 { float x, y, z, w; };
 struct int4 { int x, y, z, w; };
+struct uint4 { unsigned x, y, z, w; };
+inline int min(int a, int b) { return a < b ? a : b; }
 inline float4 make_float4(float x, float y, float z, float w) { float4 r = {x, y, z, w}; return r; }
 
 template <typename T> inline T __ldg(const T* p) { return *p; }

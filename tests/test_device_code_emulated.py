@@ -17,7 +17,8 @@ MAX_LEVELS = 12
 EMU_VIEW = np.dtype([("campos", "<f4", (3,)), ("inv_ax0", "<f4"), ("w2c", "<f4", (12,)), ("rot", "<f4", (9,)),
                      ("nlevels", "<i4"), ("ax", "<f4", (MAX_LEVELS,)), ("ay", "<f4", (MAX_LEVELS,)),
                      ("cx", "<f4", (MAX_LEVELS,)), ("cy", "<f4", (MAX_LEVELS,)), ("w", "<i4", (MAX_LEVELS,)),
-                     ("h", "<i4", (MAX_LEVELS,)), ("pitch", "<i4", (MAX_LEVELS,)), ("img", "<u8", (MAX_LEVELS,))], align=True)
+                     ("h", "<i4", (MAX_LEVELS,)), ("pitch", "<i4", (MAX_LEVELS,)), ("img", "<u8", (MAX_LEVELS,)),
+                     ("quad", "<u8", (MAX_LEVELS,))], align=True)
 EMU_IN = np.dtype([("x", "<i4"), ("y", "<i4"), ("depth", "<f4"), ("dzI", "<f4"), ("dzJ", "<f4"), ("slots", "<u4")])
 EMU_OUT = np.dtype([("conf", "<f4"), ("depth", "<f4"), ("dzI", "<f4"), ("dzJ", "<f4"), ("nx", "<f4"), ("ny", "<f4"),
                     ("nz", "<f4"), ("slots", "<u4"), ("iterations", "<i4"), ("flags", "<i4"), ("sets", "<u4")])
@@ -59,6 +60,13 @@ def _run(lib, s, osc, ref, gsel, settings, pin):
             rgbx[:, :w, :3] = img
             rgbx[:, :w, 3] = 255
             keep.append(rgbx)
+            # quad image (mve_b200/csrc/b200mvs.cu k_make_quads): the 2x2 neighbourhood of every texel, clamped at the border
+            t = rgbx.view(np.uint32)[:, :, 0]
+            x1 = np.minimum(np.arange(pitch) + 1, w - 1)
+            y1 = np.minimum(np.arange(h) + 1, h - 1)
+            quad = np.ascontiguousarray(np.stack([t, t[:, x1], t[y1, :], t[y1][:, x1]], -1))
+            keep.append(quad)
+            views[v]["quad"][l] = quad.ctypes.data
             views[v]["ax"][l], views[v]["ay"][l], views[v]["cx"][l], views[v]["cy"][l] = K[0], K[4], K[2], K[5]
             views[v]["w"][l], views[v]["h"][l], views[v]["pitch"][l] = w, h, pitch
             views[v]["img"][l] = rgbx.ctypes.data

