@@ -3,11 +3,14 @@
 
     python bench.py --gpus N --steps K --warmup W            # our arm (one rank per GPU under torchrun for N > 1)
     python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU dmrecon on the host cores
+    python bench.py --workload C3|C4|C5 --gpus N ...         # the other BASELINE configs (nominally 8 / 4 / 8 GPUs)
 
-Workload (N = 1): BASELINE.json configs[1] - synthetic 16-view 1920x1080 scene, dmrecon scale = 1, all 16 views
-reconstructed; one step = DMRecon::start for all 16 reference views.  N > 1: the same per-GPU work (16 reference
-views per rank, weak scaling) on a 16N-view scene; every rank renders and uploads its own shard and the images of the
-other shards arrive through one NCCL all-gather (the reference path has no other cross-view exchange).
+Workload (default, N = 1): BASELINE.json configs[1] (C2) - synthetic 16-view 1920x1080 scene, dmrecon scale = 1, all 16
+views reconstructed; one step = DMRecon::start for all 16 reference views.  N > 1: the same per-GPU work (16 reference
+views per rank, weak scaling) on a 16N-view scene of N tiled camera blocks.  C3 / C4 / C5: the scene is the config's own
+(64 / 32 / 128 views); every rank reconstructs views_total / nominal_gpus reference views (8 / 8 / 16), so the config is
+covered completely at its nominal GPU count and a shard of it below.  Every rank renders and uploads its own shard; the
+images of the other shards arrive through one NCCL all-gather (the reference path has no other cross-view exchange).
 
 value  = depth-pixels (pixels ending with conf > 0, = progress.filled) per second with the image pyramids already
          resident in HBM, results left in HBM, summed over all ranks / max-over-ranks time.
@@ -39,6 +42,9 @@ def log(*a):
 
 
 # ----------------------------------------------------------------------------------------------------------------
+NOMINAL_GPUS = {"C2": 1, "C3": 8, "C4": 4, "C5": 8}
+
+
 def workload_cfg(name, n_gpus):
     from mve_b200 import synth
     cfg = dict(synth.CONFIGS[name])
@@ -49,6 +55,21 @@ def workload_cfg(name, n_gpus):
         cfg["features"] = 4000 * n_gpus
     cfg["name"] = name
     return cfg
+
+
+def refs_of_rank(name, cfg, rank, world):
+    """Reference views reconstructed by `rank`: C2 - its block of 16; C3/C4/C5 (and test scenes) - a block of
+    views_total / nominal_gpus views (the whole config at the nominal GPU count, a shard of it below)."""
+    from mve_b200 import sharding
+    if name == "C2" or name not in NOMINAL_GPUS:
+        return sharding.owned_views(cfg["views"], rank, world)
+    per = max(1, cfg["views"] // NOMINAL_GPUS[name])
+    lo = min(rank * per, cfg["views"])
+    return list(range(lo, min(lo + per, cfg["views"])))
+
+
+def workload_text(name, scene):
+    return "%s: synthetic %d-view %dx%d scene, dmrecon scale=%d" % (name, scene.n_views, scene.width, scene.height, scene.scale)
 
 
 class ClockSampler:
@@ -122,30 +143,54 @@ def _cuda_ok():
         return False
 
 
-def run_reference_sample(scene_dir, scene, seconds, views):
-    """One bounded sample of the reference CPU path. Returns (filled_px, elapsed_s, threads, kind, sample_text)."""
+REF_VIEWS_MAX = 16     # the reference arm times a fixed subset of <= 16 reference views: one thread per view
+
+
+def run_reference_samples(scene_dir, scene, seconds, views, steps):
+    """`steps` bounded samples of the reference CPU path in ONE process. Returns (list of (filled_px, elapsed_s), threads,
+    kind, sample_text)."""
     harness = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
     if os.path.exists(harness):
-        cmd = [harness, "timed", scene_dir, str(scene.scale), str(scene.nr_recon_neighbors), "%.3f" % seconds] + [str(v) for v in views]
-        out = subprocess.run(cmd, capture_output=True, text=True, check=True).stdout.strip().splitlines()[-1]
-        r = json.loads(out)
-        return r["filled"], r["seconds"], len(views), "reference", \
-            "oracle/_ref/ref_harness timed: mvs::DMRecon::start of %d reference views on %d host threads (one per view, " \
-            "apps/dmrecon.cc:285), cancelled after %.1f s through Progress::cancelled; images pre-loaded" % (len(views), len(views), seconds)
+        cmd = [harness, "timed", scene_dir, str(scene.scale), str(scene.nr_recon_neighbors), "%.3f" % seconds, str(steps)] + [str(v) for v in views]
+        out = subprocess.run(cmd, capture_output=True, text=True, check=True).stdout.strip().splitlines()
+        rows = [json.loads(l) for l in out if l.startswith("{")]
+        return [(r["filled"], r["seconds"]) for r in rows], len(views), "reference", \
+            "oracle/_ref/ref_harness timed (the unmodified reference, built -O3 -march=x86-64-v3 -funsafe-math-optimizations; " \
+            "-march=native is not used because the binary travels): mvs::DMRecon::start of reference views %s on %d host " \
+            "threads (one per view, apps/dmrecon.cc:285); clock from the moment every view has reached processQueue " \
+            "(RECON_QUEUE) until Progress::cancelled is set %.1f s later; images pre-loaded, pyramids cached" % (
+                views, len(views), seconds)
     # the compiled reference is not here: fall back to the CPU port, one thread per view
     from oracle import oracle_py as O
     osc = O.OracleScene(scene)
     st = O.default_settings(scale=scene.scale, nr_recon_neighbors=scene.nr_recon_neighbors)
-    filled = [0] * len(views)
+    rows = []
+    for _ in range(steps):
+        filled = [0] * len(views)
 
-    def work(k, v):
-        filled[k] = int(osc.reconstruct(st, v, max_seconds=seconds)["stats"]["n_filled"])
-    t0 = time.time()
-    th = [threading.Thread(target=work, args=(k, v)) for k, v in enumerate(views)]
-    [t.start() for t in th]
-    [t.join() for t in th]
-    return sum(filled), time.time() - t0, len(views), "port", \
-        "oracle/mvs_oracle.cc port, %d views on %d threads, stopped after %.1f s" % (len(views), len(views), seconds)
+        def work(k, v):
+            filled[k] = int(osc.reconstruct(st, v, max_seconds=seconds)["stats"]["n_filled"])
+        t0 = time.time()
+        th = [threading.Thread(target=work, args=(k, v)) for k, v in enumerate(views)]
+        [t.start() for t in th]
+        [t.join() for t in th]
+        rows.append((sum(filled), time.time() - t0))
+    return rows, len(views), "port", "oracle/mvs_oracle.cc port, %d views on %d threads, stopped after %.1f s" % (len(views), len(views), seconds)
+
+
+def reference_views(name, cfg, cores):
+    """Fixed subset of reference views timed on the CPU: the first block (= the N = 1 workload's views), at most
+    REF_VIEWS_MAX and at most one per host core."""
+    first = refs_of_rank(name, cfg, 0, max(1, NOMINAL_GPUS.get(name, 1)) if name != "C2" else max(1, cfg.get("blocks", 1)))
+    return first[:max(1, min(REF_VIEWS_MAX, cores, len(first)))]
+
+
+def cpu_baseline_dict(value, threads, kind, sample, cores, n_views):
+    return {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample,
+            "px_per_s_per_core": value / max(1, threads), "host_cores_available": cores,
+            "threads_usable_on_this_workload": min(n_views, cores),
+            "note": "the reference's parallelism is one thread per reference view (apps/dmrecon.cc:285); a fixed subset of "
+                    "views is timed so that the figure does not depend on the number of GPUs"}
 
 
 def reference_arm(args, real_stdout):
@@ -154,26 +199,24 @@ def reference_arm(args, real_stdout):
         return 0
     cfg = workload_cfg(args.workload, max(1, args.gpus))     # the same scene our arm reconstructs at this N
     cores = host_cores()
-    budget = min(20.0, max(3.0, 150.0 / max(1, args.steps + args.warmup)))
+    n_samples = args.steps + args.warmup
+    budget = min(20.0, max(2.0, 150.0 / max(1, n_samples)))
     with tempfile.TemporaryDirectory(prefix="b200mvs_ref_") as tmp:
         t = time.time()
         scene = write_scene_for_reference(cfg, None, tmp)
-        log("reference arm: scene written in %.1fs, %d host cores, %.1fs per step" % (time.time() - t, cores, budget))
-        views = list(range(min(scene.n_views, cores)))
-        vals, secs = [], []
-        for i in range(args.warmup + args.steps):
-            filled, el, threads, kind, sample = run_reference_sample(tmp, scene, budget, views)
-            log("  step %d: %d px in %.2fs" % (i, filled, el))
-            if i >= args.warmup:
-                vals.append(filled); secs.append(el)
-    value = sum(vals) / sum(secs)
+        views = reference_views(args.workload, cfg, cores)
+        log("reference arm: scene written in %.1fs, %d host cores, views %s, %.1fs per step" % (time.time() - t, cores, views, budget))
+        rows, threads, kind, sample = run_reference_samples(tmp, scene, budget, views, n_samples)
+    for i, (f, el) in enumerate(rows):
+        log("  step %d: %d px in %.2fs" % (i, f, el))
+    rows = rows[args.warmup:]
+    value = sum(f for f, _ in rows) / sum(el for _, el in rows)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * sum(secs) / len(secs), "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": 1e3 * sum(el for _, el in rows) / len(rows), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "%s: synthetic %d-view %dx%d scene, dmrecon scale=%d" % (args.workload, scene.n_views, scene.width, scene.height, scene.scale),
-                       "step": "time-boxed sample of the same workload (reference cannot finish a step within the run budget)"},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample,
-                             "host_cores_available": cores},
+            "config": {"workload": workload_text(args.workload, scene),
+                       "step": "time-boxed sample of the same workload: %d of its reference views on %d host threads" % (len(views), threads)},
+            "cpu_baseline": cpu_baseline_dict(value, threads, kind, sample, cores, scene.n_views),
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), file=real_stdout, flush=True)
@@ -232,7 +275,8 @@ def _main(real_stdout):
         dist.init_process_group("nccl", device_id=dev)
 
     cfg = workload_cfg(args.workload, world)
-    owned = sharding.owned_views(cfg["views"], rank, world)
+    owned = sharding.owned_views(cfg["views"], rank, world)      # views this rank renders / uploads (every view has one owner)
+    refs = refs_of_rank(args.workload, cfg, rank, world)          # reference views this rank reconstructs
     t0 = time.time()
     scene = synth.make_scene(cfg, device=str(dev), only_views=owned)
     log("[rank %d] scene %s: %d views (%d owned) generated in %.1fs" % (rank, args.workload, scene.n_views, len(owned), time.time() - t0))
@@ -250,8 +294,8 @@ def _main(real_stdout):
     # reference views and of their selected neighbours are turned into pyramids on this GPU.
     for v in range(scene.n_views):
         gscene.set_view_camera(v, W, H, scene.flen[v], scene.paspect[v], scene.ppoint[v], scene.rot[v], scene.trans[v])
-    needed = set(owned)
-    for r in owned:
+    needed = set(refs)
+    for r in refs:
         needed.update(gscene.global_view_selection(settings, r))
     needed = sorted(needed)
     log("[rank %d] %d of %d views needed on this GPU" % (rank, len(needed), scene.n_views))
@@ -271,7 +315,7 @@ def _main(real_stdout):
     for _ in range(scene.scale):
         Ws, Hs = (Ws + 1) // 2, (Hs + 1) // 2
     out_bufs = []
-    for _ in owned:
+    for _ in refs:
         out_bufs.append(dict(depth=torch.empty((Hs, Ws), dtype=torch.float32).pin_memory().numpy(),
                              conf=torch.empty((Hs, Ws), dtype=torch.float32).pin_memory().numpy(),
                              dz=torch.empty((Hs, Ws, 2), dtype=torch.float32).pin_memory().numpy()))
@@ -283,15 +327,26 @@ def _main(real_stdout):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # The host part of DMRecon::start (global view selection + seed lists, dmrecon.cc:179-292) of the NEXT step's views is
+    # computed on a helper thread while the GPU runs the current step (b200mvs_plan_views) - every step still computes it
+    # once, it is just not serialised with the kernel, like consecutive batches of a real scene.
+    import concurrent.futures
+    planner = concurrent.futures.ThreadPoolExecutor(max_workers=1)
+    pending = [planner.submit(gscene.plan_views, settings, refs)]
+
     def step_resident():
         flush.zero_()
-        _, st = gscene.reconstruct(settings, owned, download=False)
+        pending.pop().result()
+        pending.append(planner.submit(gscene.plan_views, settings, refs))
+        _, st = gscene.reconstruct(settings, refs, download=False)
         return st
 
     def step_e2e():
         flush.zero_()
+        pending.pop().result()
+        pending.append(planner.submit(gscene.plan_views, settings, refs))
         upload_all()
-        _, st = gscene.reconstruct(settings, owned, download=True, out=out_bufs)
+        _, st = gscene.reconstruct(settings, refs, download=True, out=out_bufs)
         return st
 
     def agg(x):
@@ -320,10 +375,12 @@ def _main(real_stdout):
     _, dev_ms_max = agg(sum(s.ms_total_device for s in stats))
     value = filled_total / elapsed_max
     launches_total, _ = agg(sum(int(s.n_kernel_launches) for s in stats))
+    refs_total, _ = agg(len(refs))
 
     # ---- end to end through the host-buffer API ----
-    e2e_steps = max(1, min(args.steps, 3))
-    step_e2e()
+    e2e_steps = args.steps
+    for _ in range(min(2, args.warmup)):
+        step_e2e()
     barrier()
     t0 = time.perf_counter()
     f_e2e = 0
@@ -335,8 +392,10 @@ def _main(real_stdout):
     _, e2e_max = agg(e2e_elapsed)
     h2d = int(host_imgs.numel())
     d2h = int(sum(b["depth"].nbytes + b["conf"].nbytes + b["dz"].nbytes for b in out_bufs))
+    pending.pop().result()
+    planner.shutdown()
 
-    # ---- roofline of the dominant kernel (k_optimize), rank 0 ----
+    # ---- roofline of the dominant kernel (k_frontier: the persistent kernel that runs every PatchOptimization), rank 0 ----
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -351,31 +410,35 @@ def _main(real_stdout):
         pass
     bpp = float(consts.get("bytes_alg_per_filled_px", 0.0))
     ms_kernel = sum(s.ms_patch_kernel for s in stats)
+    ms_opt = sum(s.ms_optimise_phases for s in stats)
     n_launch = sum(int(s.n_patch_launches) for s in stats)
     achieved = (bpp * filled_local / (ms_kernel * 1e-3)) / 1e9 if ms_kernel > 0 and bpp > 0 else None
     traffic, traffic_src, ncu_context = None, None, None
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_kopt_final_traffic.json")))
-        traffic = tj["dram_bytes_per_launch_mean"]
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r2_kfrontier_traffic.json")))
+        traffic = tj["dram_bytes_per_launch"]
         ncu_context = tj.get("ncu_context")
-        traffic_src = "ncu --set full capture of %d mid-run launches (%.0f patches each): profiles/r1_kopt_final_traffic.json" % (
-            len(tj["launches"]), tj["patches_per_launch_mean"])
+        traffic_src = tj.get("source")
     except Exception:
         pass
-    roofline = {"kernel": "k_optimize (patch optimisation, one warp per queue entry)", "bound": "hbm",
+    roofline = {"kernel": "k_frontier (persistent cooperative kernel: seeds + every frontier round of the step in one launch; "
+                          "8 lanes per patch)", "bound": "hbm",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                 "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_filled_px": bpp,
                 "definition": "300 B x N_PSE + 75 B x N_opt + 28 B x N_filled with the oracle's strict-order counts per filled "
                               "pixel (profiles/scene_constants_%s.json) x filled pixels of the launch, / CUDA-event time of the "
-                              "k_optimize launches in the timed region" % args.workload,
+                              "k_frontier launches in the timed region (one launch per step)" % args.workload,
                 "avg_launch_ms": ms_kernel / max(1, n_launch), "launches": n_launch,
                 "algorithmic_bytes_per_launch_mean": (bpp * filled_local / max(1, n_launch)) if bpp > 0 else None,
                 "kernel_share_of_device_time": ms_kernel / max(1e-9, sum(s.ms_total_device for s in stats)),
+                "optimise_phase_share_of_kernel": ms_opt / max(1e-9, ms_kernel),
+                "frontier_rounds_per_launch": sum(int(s.n_rounds) for s in stats) / max(1, n_launch),
+                "grid_barriers_per_launch": sum(int(s.n_grid_barriers) for s in stats) / max(1, n_launch),
                 "impl_sample_sets": sum(int(s.n_sample_sets) for s in stats), "impl_opts": sum(int(s.n_opt) for s in stats),
                 "impl_bytes_300_per_set_GBs": (300.0 * sum(int(s.n_sample_sets) for s in stats) / (ms_kernel * 1e-3) / 1e9) if ms_kernel > 0 else None}
     if ncu_context:
-        roofline["ncu_context"] = ncu_context      # what actually bounds the kernel (issue slots / L1), from the committed capture
+        roofline["ncu_context"] = ncu_context      # what actually bounds the kernel, from the committed capture
     # context only: the same launches against the fp32 SIMT peak with SURVEY.md 8(d)'s ~110 kFLOP per reference
     # PatchOptimization (oracle count per filled pixel x filled pixels)
     opf = float(consts.get("opt_per_filled_px", 0.0))
@@ -384,31 +447,34 @@ def _main(real_stdout):
         roofline["fp32_context"] = {"achieved_tflops": tf, "peak_tflops": 74.0, "frac": tf / 74.0,
                                     "note": "148 SM x 128 lanes x 2 x 1.965 GHz (derived, not measured); 110 kFLOP per reference optimisation"}
 
-    # ---- cpu_baseline (rank 0, N = 1 only): the reference's own CPU dmrecon on this box's host cores ----
+    # ---- cpu_baseline (rank 0): the reference's own CPU dmrecon on this box's host cores, bounded sample ----
     cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and not args.no_cpu_baseline:
         try:
             full = synth.make_scene(cfg, device=str(dev))
             with tempfile.TemporaryDirectory(prefix="b200mvs_cpu_") as tmp:
                 synth.write_mve_scene(full, tmp)
                 cores = host_cores()
-                views = list(range(min(full.n_views, cores)))
-                filled, el, threads, kind, sample = run_reference_sample(tmp, full, args.cpu_seconds, views)
-            cpu_baseline = {"value": filled / el, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample,
-                            "host_cores_available": cores}
+                views = reference_views(args.workload, cfg, cores)
+                rows, threads, kind, sample = run_reference_samples(tmp, full, args.cpu_seconds / 3.0, views, 3)
+            rows = rows[1:]                      # the first sample builds the reference's lazy pyramid levels
+            cpu_baseline = cpu_baseline_dict(sum(f for f, _ in rows) / sum(el for _, el in rows), threads, kind, sample, cores, full.n_views)
         except Exception as ex:   # the GPU numbers stand on their own
             cpu_baseline = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(ex)}
+    if world > 1:
+        barrier()
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": 1e3 * elapsed_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
-                "config": {"workload": "%s: synthetic %d-view %dx%d scene, dmrecon scale=%d, %d reference views per GPU" %
-                                       (args.workload, scene.n_views, W, H, scene.scale, len(owned)),
+                "config": {"workload": workload_text(args.workload, scene),
+                           "reference_views_per_gpu": len(refs), "reference_views_total": int(refs_total),
                            "sharding": "reference views block-sharded over ranks; image shards exchanged by one NCCL all-gather" if world > 1 else "single GPU",
-                           "l2": "256 MiB buffer written between steps (L2 flush); the pyramids alone (%.0f MB) exceed the 126 MB L2" %
-                                 (scene.n_views * W * H * 4 * 4 / 3 / 1e6),
-                           "filled_px_per_step": filled_total / args.steps, "swept_px_per_step": world * len(owned) * Ws * Hs,
+                           "l2": "256 MiB buffer written between steps (L2 flush); the pyramids alone (%.0f MB incl. quad texels) exceed the 126 MB L2" %
+                                 (len(needed) * W * H * 20 * 4 / 3 / 1e6),
+                           "host_phase": "global view selection + seed lists of step k+1 are computed on a helper thread while the GPU runs step k (b200mvs_plan_views)",
+                           "filled_px_per_step": filled_total / args.steps, "swept_px_per_step": int(refs_total) * Ws * Hs,
                            "device_ms_per_step_max": dev_ms_max / args.steps},
                 "clocks": clocks, "gpu_launches": int(launches_total),
                 "e2e": {"value": f_e2e_total / e2e_max, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

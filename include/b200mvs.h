@@ -170,6 +170,14 @@ int b200mvs_get_level(b200mvs_ctx* ctx, int view_id, int level, int* w, int* h, 
 int b200mvs_global_view_selection(b200mvs_ctx* ctx, const b200mvs_settings* s, int ref_view,
                                   int32_t* ids_out, int cap);
 
+/* Prepares, on host threads, what DMRecon::start computes before its queue runs - analyzeFeatures, globalViewSelection and
+ * the seed list of processFeatures (dmrecon.cc:179-292) - for the given reference views, so that a LATER
+ * b200mvs_reconstruct of these views (same settings) starts its kernel at once.  May be called from another thread WHILE a
+ * b200mvs_reconstruct of a previous batch is running (the reference overlaps them the same way: its OpenMP threads are in
+ * different stages of different views, apps/dmrecon/dmrecon.cc:285); cameras and features must not change meanwhile.
+ * A plan is used once and dropped; changing a camera or the features drops all plans. */
+int b200mvs_plan_views(b200mvs_ctx* ctx, const b200mvs_settings* s, int n_refs, const int32_t* ref_views);
+
 /* ---- batch of independent PatchOptimization runs: ctor + doAutoOptimization + computeConfidence
  *      (patch_optimization.cc:21-242); the patch-level parity entry ---- */
 int b200mvs_optimize_patches(b200mvs_ctx* ctx, const b200mvs_settings* s, int ref_view,

@@ -8,6 +8,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <chrono>
 #include <ctime>
 #include <mutex>
@@ -42,6 +43,13 @@ struct HostView {
     std::vector<HostLevel> lv;
     uchar4* d_base = nullptr;      // one allocation for every level: the RGBX8 images, then their quad images
     size_t bytes = 0;
+};
+
+struct SeedPoint { int x, y; float depth; };
+struct HostPlan {                  // what DMRecon::start computes on the host before the queue runs (dmrecon.cc:179-292)
+    b200mvs_settings settings;     // the settings it was made for
+    std::vector<int> gsel;         // globalViewSelection result, ascending
+    std::vector<SeedPoint> seeds;  // the feature loop of processFeatures
 };
 
 struct HostFeature {
@@ -129,6 +137,14 @@ struct b200mvs_ctx {
     unsigned long long* h_counters = nullptr;   // pinned
     unsigned long long* h_mirror = nullptr;     // pinned + mapped: HostMirror
     std::vector<cudaEvent_t> ev_pool;
+    // b200mvs_upload_view staging: two pinned host buffers + device buffers used alternately, so that the host copy of
+    // view k+1 overlaps the H2D transfer and the pyramid kernels of view k
+    struct Stage { uint8_t* host = nullptr; uint8_t* dev = nullptr; size_t cap = 0; cudaEvent_t done = nullptr; bool busy = false; };
+    Stage stage[2];
+    unsigned stage_next = 0;
+    // host plans prepared ahead by b200mvs_plan_views (global view selection + seed list of a reference view)
+    std::mutex plan_mtx;
+    std::map<int, HostPlan> plans;
 };
 
 namespace {
@@ -322,7 +338,7 @@ std::vector<int> global_view_selection(const b200mvs_ctx* c, const b200mvs_setti
     return selected;
 }
 
-struct Seed { int x, y; float depth; };
+using Seed = SeedPoint;
 
 // The feature loop of DMRecon::processFeatures (dmrecon.cc:258-292): which features seed, at which pixel, with
 // which initial depth.  The optimisation of the seeds runs on the device.
@@ -439,12 +455,12 @@ __global__ void k_export_rgb(const uchar4* __restrict__ src, int w, int h, int p
 #define OPT_TPB 256          // threads per CTA of the patch-optimisation kernels (32 patch groups of 8 lanes)
 #endif
 #ifndef OPT_MIN_BLOCKS
-#define OPT_MIN_BLOCKS 2     // CTAs per SM: registers per thread <= 65536 / (OPT_MIN_BLOCKS * OPT_TPB); shared memory 80 KB per CTA
+#define OPT_MIN_BLOCKS 2     // CTAs per SM: registers per thread <= 65536 / (OPT_MIN_BLOCKS * OPT_TPB); shared memory 32 KB per CTA
 #endif
 constexpr int OPT_WARPS = OPT_TPB / 32;
-// dynamic shared memory of the kernels that optimise patches: the replicated sRGB table + the per-thread arrays of Patch
-constexpr size_t OPT_SMEM_BYTES = sizeof(float) * (256 * LUT_REP + PRIV_WORDS * OPT_TPB);
-using PatchT = Patch<OPT_TPB>;
+// dynamic shared memory of the kernels that optimise patches: the lane-replicated sRGB table
+constexpr size_t OPT_SMEM_BYTES = sizeof(float) * (256 * LUT_REP);
+using PatchT = Patch;
 
 __device__ __forceinline__ Entry load_entry(const Entry* p)       // lists are rewritten by other SMs every round: bypass L1
 {
@@ -461,7 +477,7 @@ __device__ __forceinline__ void opt_setup(PatchT& p, float* smem, const float* g
 {
     for (int i = threadIdx.x; i < 256 * LUT_REP; i += blockDim.x) smem[i] = g_lut[i / LUT_REP];
     __syncthreads();
-    bind_thread(p, st, views, smem, smem + 256 * LUT_REP, (int)threadIdx.x);
+    bind_thread(p, st, views, smem, (int)threadIdx.x);
 }
 
 // The PatchOptimizations of list[0..n): every 8-lane group takes entries through the ticket counter until none is left; a
@@ -872,6 +888,12 @@ int upload_common(b200mvs_ctx* ctx, int id, const uint8_t* d_src, int w, int h, 
                   const float* pp, const float* rot, const float* trans, cudaStream_t stream)
 {
     HostView& v = ctx->views[id];
+    {
+        // prepared plans depend on cameras and image sizes only: a re-upload of the same view with the same camera keeps them
+        const bool same = v.valid && v.w == w && v.h == h && v.flen == flen && v.paspect == paspect && v.pp[0] == pp[0] && v.pp[1] == pp[1] &&
+                          std::memcmp(v.rot, rot, sizeof(v.rot)) == 0 && std::memcmp(v.trans, trans, sizeof(v.trans)) == 0;
+        if (!same) { std::lock_guard<std::mutex> pl(ctx->plan_mtx); ctx->plans.clear(); }
+    }
     v.valid = false;
     v.has_image = false;
     v.w = w; v.h = h; v.flen = flen; v.paspect = paspect; v.pp[0] = pp[0]; v.pp[1] = pp[1];
@@ -1093,6 +1115,11 @@ void b200mvs_destroy(b200mvs_ctx* ctx)
     if (ctx->d_lut) cudaFree(ctx->d_lut);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     if (ctx->h_mirror) cudaFreeHost(ctx->h_mirror);
+    for (b200mvs_ctx::Stage& S : ctx->stage) {
+        if (S.host) cudaFreeHost(S.host);
+        if (S.dev) cudaFree(S.dev);
+        if (S.done) cudaEventDestroy(S.done);
+    }
     ctx->ent_a.release(); ctx->ent_b.release(); ctx->run_in.release(); ctx->run_out.release(); ctx->written.release();
     ctx->counters.release(); ctx->d_jobs.release(); ctx->d_settings.release(); ctx->maps.release();
     ctx->ctl.release(); ctx->hist.release(); ctx->thr_bin.release();
@@ -1111,15 +1138,24 @@ int b200mvs_upload_view(b200mvs_ctx* ctx, int id, const uint8_t* rgb, int w, int
         return fail(ctx, B200MVS_ERR_INVALID_ARG, "b200mvs_upload_view: bad arguments");
     if (channels < 1 || channels > 4) return fail(ctx, B200MVS_ERR_INVALID_ARG, "Image with invalid number of channels");
     CK(cudaSetDevice(ctx->device));
-    uint8_t* d_src = nullptr;
     const size_t bytes = (size_t)w * h * channels;
-    CK(cudaMalloc(&d_src, bytes));
-    cudaError_t e = cudaMemcpyAsync(d_src, rgb, bytes, cudaMemcpyHostToDevice, ctx->stream);
-    int rc = 0;
-    if (e != cudaSuccess) rc = fail(ctx, B200MVS_ERR_CUDA, "cudaMemcpyAsync: %s", cudaGetErrorString(e));
-    if (!rc) rc = upload_common(ctx, id, d_src, w, h, channels, flen, paspect, ppoint, rot, trans, ctx->stream);
-    cudaStreamSynchronize(ctx->stream);
-    cudaFree(d_src);
+    b200mvs_ctx::Stage& S = ctx->stage[ctx->stage_next++ & 1u];
+    if (S.busy) { CK(cudaEventSynchronize(S.done)); S.busy = false; }      // the transfer that used this slot two uploads ago
+    if (S.cap < bytes) {
+        if (S.host) cudaFreeHost(S.host);
+        if (S.dev) cudaFree(S.dev);
+        S.host = nullptr; S.dev = nullptr; S.cap = 0;
+        CK(cudaMallocHost(&S.host, bytes));
+        CK(cudaMalloc(&S.dev, bytes));
+        S.cap = bytes;
+    }
+    if (!S.done) CK(cudaEventCreateWithFlags(&S.done, cudaEventDisableTiming));
+    std::memcpy(S.host, rgb, bytes);                                         // pageable -> pinned; returns the caller's buffer
+    CK(cudaMemcpyAsync(S.dev, S.host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    const int rc = upload_common(ctx, id, S.dev, w, h, channels, flen, paspect, ppoint, rot, trans, ctx->stream);
+    CK(cudaEventRecord(S.done, ctx->stream));
+    S.busy = true;
+    // no synchronisation here: everything that reads the pyramid is ordered behind it on the context's stream
     return rc;
 }
 
@@ -1156,6 +1192,7 @@ int b200mvs_set_features(b200mvs_ctx* ctx, int n, const float* pos, const int32_
     if (!ctx) return B200MVS_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> lk(ctx->mtx);
     if (n < 0 || (n > 0 && (!pos || !off || !ids))) return fail(ctx, B200MVS_ERR_INVALID_ARG, "b200mvs_set_features: bad arguments");
+    { std::lock_guard<std::mutex> pl(ctx->plan_mtx); ctx->plans.clear(); }
     ctx->feats.resize(n);
     for (int i = 0; i < n; ++i) {
         std::memcpy(ctx->feats[i].pos, pos + 3 * i, 12);
@@ -1214,6 +1251,38 @@ int b200mvs_global_view_selection(b200mvs_ctx* ctx, const b200mvs_settings* s, i
     std::vector<int> sel = global_view_selection(ctx, *s, ref);
     for (int i = 0; i < (int)sel.size() && i < cap; ++i) ids_out[i] = sel[i];
     return (int)sel.size();
+}
+
+int b200mvs_plan_views(b200mvs_ctx* ctx, const b200mvs_settings* s, int n_refs, const int32_t* refs)
+{
+    if (!ctx) return B200MVS_ERR_INVALID_ARG;
+    // Deliberately NOT under ctx->mtx: planning reads only cameras and features and may overlap a running
+    // b200mvs_reconstruct of another batch (the caller must not change cameras / features meanwhile).
+    if (!s || n_refs < 0 || (n_refs > 0 && !refs)) return B200MVS_ERR_INVALID_ARG;
+    if (s->filter_width != 5 || s->scale < 0 || s->global_vs_max < 1 || s->global_vs_max > B200MVS_MAX_GLOBAL_VIEWS) return B200MVS_ERR_INVALID_ARG;
+    std::vector<HostPlan> made(n_refs);
+    std::atomic<int> next_job(0);
+    std::atomic<int> bad(0);
+    auto worker = [&]() {
+        for (;;) {
+            const int j = next_job.fetch_add(1);
+            if (j >= n_refs) break;
+            const int r = refs[j];
+            if (r < 0 || r >= (int)ctx->views.size() || !ctx->views[r].valid || s->scale >= (int)ctx->views[r].lv.size()) { bad = 1; continue; }
+            made[j].settings = *s;
+            made[j].gsel = global_view_selection(ctx, *s, r);
+            if (!made[j].gsel.empty()) made[j].seeds = collect_seeds(ctx, *s, r, made[j].gsel);
+        }
+    };
+    const int n_threads = std::max(1, std::min<int>(n_refs, (int)std::thread::hardware_concurrency()));
+    std::vector<std::thread> pool;
+    for (int t = 1; t < n_threads; ++t) pool.emplace_back(worker);
+    worker();
+    for (std::thread& t : pool) t.join();
+    if (bad) return B200MVS_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> pl(ctx->plan_mtx);
+    for (int j = 0; j < n_refs; ++j) ctx->plans[refs[j]] = std::move(made[j]);
+    return 0;
 }
 
 int b200mvs_optimize_patches(b200mvs_ctx* ctx, const b200mvs_settings* s, int ref, const int32_t* gids, int ng,
@@ -1345,6 +1414,18 @@ int b200mvs_reconstruct(b200mvs_ctx* ctx, const b200mvs_settings* s, int n_refs,
                 const int j = next_job.fetch_add(1);
                 if (j >= n_refs) break;
                 if (progress) { progress[j].status = 1; progress[j].start_time = (uint64_t)t_start; progress[j].filled = 0; progress[j].queue_size = 0; }
+                {
+                    // a plan prepared ahead (b200mvs_plan_views, possibly while the previous batch was running) is used once
+                    std::lock_guard<std::mutex> pl(ctx->plan_mtx);
+                    auto it = ctx->plans.find(refs[j]);
+                    if (it != ctx->plans.end() && std::memcmp(&it->second.settings, s, sizeof(*s)) == 0) {
+                        gsels[j] = std::move(it->second.gsel);
+                        seed_lists[j] = std::move(it->second.seeds);
+                        ctx->plans.erase(it);
+                        if (progress) progress[j].status = 2;
+                        continue;
+                    }
+                }
                 gsels[j] = global_view_selection(ctx, *s, refs[j]);
                 if (gsels[j].empty()) continue;
                 if (progress) progress[j].status = 2;

@@ -17,10 +17,10 @@
 //     groups of a warp run different patches, in different stages, and re-converge at the one pass() call
 //     site; a group that finishes fetches its next patch without waiting for the others (Patch::begin /
 //     step / finish are driven by a flat loop in the kernels);
-//   * the loop over a lane's sample slots is ROLLED (the sampling code exists once in the instruction
-//     stream, profiles/r1_notes.md explains why that matters); what must survive between the slots of a
-//     sample set - rays, master colours, the drawn colours and derivatives - lives in shared memory,
-//     one word per thread and array element, bank-conflict free;
+//   * a lane's four sample slots are unrolled: rays, master colours, drawn colours and derivatives of its samples stay in
+//     registers between the sampling and the reductions that consume them (a rolled variant that kept them in shared
+//     memory spent as many instructions re-reading them as on sampling, profiles/r2_notes.md); the four independent
+//     sample computations give the scheduler instruction-level parallelism to hide the texel loads;
 //   * the four bilinear taps of a sample come from ONE 16-byte load of a "quad" texel (the 2x2 neighbourhood
 //     of every pixel is stored contiguously, DESIGN.md "Data layout"); sRGB code values are linearised through a
 //     copy of the 256-entry table that is replicated per lane (no bank conflicts, mvs_tools.cc:21-95);
@@ -47,8 +47,6 @@ constexpr int CENTER = 12;   // patch_sampler.cc:73,96
 constexpr int GROUP = 8;     // lanes per patch
 constexpr int SLOTS = 4;     // sample slots per lane: slot 0 = samples 24.. (+ two helper points), slot s = samples 8(s-1)..8(s-1)+7
 constexpr int LUT_REP = 32;  // replicas of the sRGB table in shared memory (one per lane)
-// per-thread words in shared memory (element e of thread t at priv[e * TPB + t])
-constexpr int PW_RAY = 0, PW_M = 12, PW_N = 24, PW_D = 36, PRIV_WORDS = 48;
 
 struct alignas(16) LevelParams {   // ImagePyramidLevel (image_pyramid.h:28-59): K = [ax 0 cx; 0 ay cy; 0 0 1]
     float ax, ay, cx, cy;
@@ -106,15 +104,18 @@ __device__ __forceinline__ float rcp_fast(float x) { float r; asm("rcp.approx.ft
 __device__ __forceinline__ float rsqrt_fast(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 #endif
 
-// TPB = threads per block (stride of the per-thread arrays in shared memory)
-template <int TPB>
 struct Patch {
     // ---- constants of the thread ----
     const DevSettings* st;
     const ViewParams* views;
     const float* lutw;         // replicated srgb2lin table + lane: value v of this lane at lutw[v * LUT_REP]
-    float* priv;               // this thread's column of the per-thread arrays
     int gl;                    // lane within the group
+    float fi[SLOTS], fj[SLOTS];   // patch offsets of the lane's samples (patch_optimization.cc:56-64), 0 for the helper points
+    // ---- per-lane sample state ----
+    float ray[SLOTS][3];       // masterViewDirs[k]
+    float mc[SLOTS][3];        // masterColorSamples[k] (normalised)
+    float sn[SLOTS][3];        // neighColorSamples[k] of the sample set drawn last
+    float sd[SLOTS][3];        // its colour derivatives along the ray
     unsigned gmask;            // lanes of the group
     // ---- constants of the patch ----
     const JobParams* job;
@@ -178,9 +179,6 @@ struct Patch {
         return (b >> (__ffs(gmask) - 1)) & 0xFFu;
     }
 
-    // ---- per-thread arrays in shared memory ----
-    __device__ __forceinline__ float& pw(int e) const { return priv[e * TPB]; }
-
     // sample handled by (slot s, this lane): index, kind and patch offsets (patch_optimization.cc:56-64)
     __device__ __forceinline__ int sample_index(int s) const { return s == 0 ? 24 + gl : (s - 1) * GROUP + gl; }
     __device__ __forceinline__ bool is_real(int s) const { return s != 0 || gl == 0; }
@@ -202,11 +200,9 @@ struct Patch {
     __device__ __forceinline__ void compute_points()
     {
         bool bad = false;
-#pragma unroll 1
+#pragma unroll
         for (int s = 0; s < SLOTS; ++s) {
-            const int k = sample_index(s);
-            const float fi = (float)(k % 5 - 2), fj = (float)(k / 5 - 2);
-            const float t = depth + fi * dzI + fj * dzJ;
+            const float t = depth + fi[s] * dzI + fj[s] * dzJ;
             bad |= is_real(s) && (t <= 0.f);
         }
         if (gany(bad)) ref_ok = false;
@@ -225,12 +221,13 @@ struct Patch {
         mx0 = mx1 = mx2 = 0.f;
         crx = cry = crz = cpx = cpy = cpz = mfp = inv_mfp = 0.f;
         if (x - 2 < 0 || y - 2 < 0 || x + 2 > job->W - 1 || y + 2 > job->H - 1) return;
+        const float r0 = __ldg(&rv->rot[0]), r1 = __ldg(&rv->rot[1]), r2 = __ldg(&rv->rot[2]), r3 = __ldg(&rv->rot[3]), r4 = __ldg(&rv->rot[4]);
+        const float r5 = __ldg(&rv->rot[5]), r6 = __ldg(&rv->rot[6]), r7 = __ldg(&rv->rot[7]), r8 = __ldg(&rv->rot[8]);
         float sum = 0.f;
-#pragma unroll 1
+#pragma unroll
         for (int s = 0; s < SLOTS; ++s) {
-            const int k = sample_index(s);
             const bool real = is_real(s);
-            const int di = real ? k % 5 - 2 : 0, dj = real ? k / 5 - 2 : 0;
+            const int di = (int)fi[s], dj = (int)fj[s];
             // viewRayScaled (single_view.cc:99-106, depthmap.cc:149-156)
             const float fx = (float)(x + di) + 0.5f, fy = (float)(y + dj) + 0.5f;
             float vx = job->ki0 * fx + job->ki2;
@@ -238,38 +235,34 @@ struct Patch {
             float vz = 1.0f;
             const float nrm = sqrtf(vx * vx + vy * vy + vz * vz);
             vx /= nrm; vy /= nrm; vz /= nrm;
-            const float rx = __ldg(&rv->rot[0]) * vx + __ldg(&rv->rot[3]) * vy + __ldg(&rv->rot[6]) * vz;
-            const float ry = __ldg(&rv->rot[1]) * vx + __ldg(&rv->rot[4]) * vy + __ldg(&rv->rot[7]) * vz;
-            const float rz = __ldg(&rv->rot[2]) * vx + __ldg(&rv->rot[5]) * vy + __ldg(&rv->rot[8]) * vz;
-            pw(PW_RAY + 3 * s) = rx; pw(PW_RAY + 3 * s + 1) = ry; pw(PW_RAY + 3 * s + 2) = rz;
-            if (s == 2) {                                 // sample 12 = slot 2, lane 4
-                crx = gbcast(rx, CENTER - GROUP); cry = gbcast(ry, CENTER - GROUP); crz = gbcast(rz, CENTER - GROUP);
-            }
+            ray[s][0] = r0 * vx + r3 * vy + r6 * vz;
+            ray[s][1] = r1 * vx + r4 * vy + r7 * vz;
+            ray[s][2] = r2 * vx + r5 * vy + r8 * vz;
             // master colours
-            float m0 = 0.f, m1 = 0.f, m2 = 0.f;
+            mc[s][0] = mc[s][1] = mc[s][2] = 0.f;
             if (real) {
                 const uchar4 t = job->ref_img[(size_t)(y + dj) * job->ref_pitch + (x + di)];
-                m0 = lutw[t.x * LUT_REP]; m1 = lutw[t.y * LUT_REP]; m2 = lutw[t.z * LUT_REP];
+                mc[s][0] = lutw[t.x * LUT_REP]; mc[s][1] = lutw[t.y * LUT_REP]; mc[s][2] = lutw[t.z * LUT_REP];
             }
-            pw(PW_M + 3 * s) = m0; pw(PW_M + 3 * s + 1) = m1; pw(PW_M + 3 * s + 2) = m2;
-            sum += m0 + m1 + m2;
+            sum += mc[s][0] + mc[s][1] + mc[s][2];
         }
+        // sample 12 = slot 2, lane 4
+        crx = gbcast(ray[2][0], CENTER - GROUP); cry = gbcast(ray[2][1], CENTER - GROUP); crz = gbcast(ray[2][2], CENTER - GROUP);
         ref_ok = true;
         mm = gsum(sum) / (3.f * NS);
         if (mm < 0.01f || mm > 0.99f) { ref_ok = false; return; }
         float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-#pragma unroll 1
+#pragma unroll
         for (int s = 0; s < SLOTS; ++s) {
-            const float m0 = pw(PW_M + 3 * s) / mm, m1 = pw(PW_M + 3 * s + 1) / mm, m2 = pw(PW_M + 3 * s + 2) / mm;
-            pw(PW_M + 3 * s) = m0; pw(PW_M + 3 * s + 1) = m1; pw(PW_M + 3 * s + 2) = m2;
-            s0 += m0; s1 += m1; s2 += m2;                 // helper points hold 0
+            mc[s][0] /= mm; mc[s][1] /= mm; mc[s][2] /= mm;
+            s0 += mc[s][0]; s1 += mc[s][1]; s2 += mc[s][2];                 // helper points hold 0
         }
         mx0 = gsum(s0) / (float)NS; mx1 = gsum(s1) / (float)NS; mx2 = gsum(s2) / (float)NS;
         float dev = 0.f;
-#pragma unroll 1
+#pragma unroll
         for (int s = 0; s < SLOTS; ++s) {
             if (!is_real(s)) continue;
-            const float e0 = pw(PW_M + 3 * s) - mx0, e1 = pw(PW_M + 3 * s + 1) - mx1, e2 = pw(PW_M + 3 * s + 2) - mx2;
+            const float e0 = mc[s][0] - mx0, e1 = mc[s][1] - mx1, e2 = mc[s][2] - mx2;
             dev += e0 * e0 + e1 * e1 + e2 * e2;
         }
         sqrDevX = gsum(dev);
@@ -285,12 +278,11 @@ struct Patch {
 
     // One fused sample set in view V at the current state: fastColAndDeriv (patch_sampler.cc:65-133 +
     // mvs_tools.cc:98-145) and computeNeighColorSamples (patch_sampler.cc:348-393 + mvs_tools.cc:169-199).
-    // Colours and derivatives of the lane's samples go to shared memory (PW_N, PW_D), sn receives the lane's partial
-    // colour sums.  Returns bit0 = colour path succeeded, bit1 = derivative path succeeded.
-    __device__ __forceinline__ unsigned sample(const ViewParams* V, float (&sn)[3])
+    // Colours and derivatives of the lane's samples go to sn / sd.  Returns bit0 = colour path succeeded,
+    // bit1 = derivative path succeeded.
+    __device__ __forceinline__ unsigned sample(const ViewParams* V)
     {
         if (gl == 0) ++n_sets;
-        sn[0] = sn[1] = sn[2] = 0.f;
         float w[12];
         {
             const float4 a = __ldg(reinterpret_cast<const float4*>(&V->w2c[0]));
@@ -317,69 +309,62 @@ struct Patch {
             L.quad = reinterpret_cast<const uint4*>(__ldg(reinterpret_cast<const unsigned long long*>(&V->lv[l].quad)));
         }
         const float c0x = __ldg(&rv->campos[0]), c0y = __ldg(&rv->campos[1]), c0z = __ldg(&rv->campos[2]);
-        float dd = 0.f, step = 0.f;
-        bool dok = false, oob = false;
-#pragma unroll 1
-        for (int s = 0; s < SLOTS; ++s) {
-            const int k = sample_index(s);
-            const bool real = is_real(s);
-            const float rx = pw(PW_RAY + 3 * s), ry = pw(PW_RAY + 3 * s + 1), rz = pw(PW_RAY + 3 * s + 2);
-            float X, Y, Z;
-            if (s == 0 && gl != 0) {
-                // helper points of the derivative step (patch_sampler.cc:94-100): lane 1 projects
-                // patchPoints[12] + masterViewDirs[12], lane 2 patchPoints[12]
-                const float a = gl == 1 ? 1.f : 0.f;
-                X = cpx + a * crx; Y = cpy + a * cry; Z = cpz + a * crz;
-            } else {
-                const float t = depth + (float)(k % 5 - 2) * dzI + (float)(k / 5 - 2) * dzJ;
-                X = c0x + t * rx; Y = c0y + t * ry; Z = c0z + t * rz;
-            }
-            float qx, qy;
-            project(w, L, X, Y, Z, qx, qy);
-            if (s == 0) {
-                const float ddx = gbcast(qx, 1) - gbcast(qx, 2);
-                const float ddy = gbcast(qy, 1) - gbcast(qy, 2);
-                const float dd2 = ddx * ddx + ddy * ddy;
-                dd = dd2 * rsqrt_fast(dd2);            // |.|; NaN for dd2 == 0, which fails `d > 0` like the reference's 0
-                dok = dd > 0.f;
-                step = rcp_fast(dd);
-            }
-            float n0 = 0.f, n1 = 0.f, n2 = 0.f, d0 = 0.f, d1 = 0.f, d2 = 0.f;
-            if (real) {
-                const bool inb = qx > 0.f && qx < (float)(L.w - 1) && qy > 0.f && qy < (float)(L.h - 1);
-                if (!inb) oob = true;
-                else {
-                    float gx = 0.f, gy = 0.f;
-                    if (dok) {
-                        float tx, ty;
-                        project(w, L, X + rx * step, Y + ry * step, Z + rz * step, tx, ty);
-                        gx = tx - qx; gy = ty - qy;
-                    }
-                    const int left = (int)floorf(qx), top = (int)floorf(qy);
-                    const float fx = qx - (float)left, fy = qy - (float)top;
-                    const uint4 Q = __ldg(L.quad + (size_t)top * L.pitch + left);
-                    float a[3], b[3], c[3], e[3];
-                    a[0] = lutw[(Q.x & 0xFF) * LUT_REP]; a[1] = lutw[((Q.x >> 8) & 0xFF) * LUT_REP]; a[2] = lutw[((Q.x >> 16) & 0xFF) * LUT_REP];
-                    b[0] = lutw[(Q.y & 0xFF) * LUT_REP]; b[1] = lutw[((Q.y >> 8) & 0xFF) * LUT_REP]; b[2] = lutw[((Q.y >> 16) & 0xFF) * LUT_REP];
-                    c[0] = lutw[(Q.z & 0xFF) * LUT_REP]; c[1] = lutw[((Q.z >> 8) & 0xFF) * LUT_REP]; c[2] = lutw[((Q.z >> 16) & 0xFF) * LUT_REP];
-                    e[0] = lutw[(Q.w & 0xFF) * LUT_REP]; e[1] = lutw[((Q.w >> 8) & 0xFF) * LUT_REP]; e[2] = lutw[((Q.w >> 16) & 0xFF) * LUT_REP];
-                    float nn[3], dv[3];
+        // projections of all slots first (slot 0 carries the two helper points of the derivative step,
+        // patch_sampler.cc:94-100: lane 1 projects patchPoints[12] + masterViewDirs[12], lane 2 patchPoints[12])
+        float X[SLOTS], Y[SLOTS], Z[SLOTS], qx[SLOTS], qy[SLOTS];
 #pragma unroll
-                    for (int ch = 0; ch < 3; ++ch) {
-                        const float x0 = (1.f - fx) * a[ch] + fx * b[ch];
-                        const float x3 = (1.f - fx) * c[ch] + fx * e[ch];
-                        nn[ch] = (1.f - fy) * x0 + fy * x3;
-                        const float der = gx * (b[ch] - a[ch]) + gy * (c[ch] - a[ch]) + (gy * fx + gx * fy) * (a[ch] - b[ch] - c[ch] + e[ch]);
-                        dv[ch] = dok ? der * dd : 0.f;        // deriv /= stepSize with stepSize = 1 / d (patch_sampler.cc:100,129-130)
-                    }
-                    n0 = nn[0]; n1 = nn[1]; n2 = nn[2]; d0 = dv[0]; d1 = dv[1]; d2 = dv[2];
-                }
+        for (int s = 0; s < SLOTS; ++s) {
+            if (s == 0) {
+                const float a = gl == 1 ? 1.f : 0.f;
+                const float t = depth + fi[0] * dzI + fj[0] * dzJ;
+                X[0] = gl == 0 ? c0x + t * ray[0][0] : cpx + a * crx;
+                Y[0] = gl == 0 ? c0y + t * ray[0][1] : cpy + a * cry;
+                Z[0] = gl == 0 ? c0z + t * ray[0][2] : cpz + a * crz;
+            } else {
+                const float t = depth + fi[s] * dzI + fj[s] * dzJ;
+                X[s] = c0x + t * ray[s][0]; Y[s] = c0y + t * ray[s][1]; Z[s] = c0z + t * ray[s][2];
             }
-            pw(PW_N + 3 * s) = n0; pw(PW_N + 3 * s + 1) = n1; pw(PW_N + 3 * s + 2) = n2;
-            pw(PW_D + 3 * s) = d0; pw(PW_D + 3 * s + 1) = d1; pw(PW_D + 3 * s + 2) = d2;
-            sn[0] += n0; sn[1] += n1; sn[2] += n2;
+            project(w, L, X[s], Y[s], Z[s], qx[s], qy[s]);
         }
+        const float ddx = gbcast(qx[0], 1) - gbcast(qx[0], 2);
+        const float ddy = gbcast(qy[0], 1) - gbcast(qy[0], 2);
+        const float dd2 = ddx * ddx + ddy * ddy;
+        const float dd = dd2 * rsqrt_fast(dd2);        // |.|; NaN for dd2 == 0, which fails `d > 0` like the reference's 0
+        const bool dok = dd > 0.f;
+        const float step = rcp_fast(dd);
+        const float wm1 = (float)(L.w - 1), hm1 = (float)(L.h - 1);
+        bool oob = false;
+#pragma unroll
+        for (int s = 0; s < SLOTS; ++s)
+            if (is_real(s) && !(qx[s] > 0.f && qx[s] < wm1 && qy[s] > 0.f && qy[s] < hm1)) oob = true;
         if (gany(oob)) return 0u;
+#pragma unroll
+        for (int s = 0; s < SLOTS; ++s) {
+            sn[s][0] = sn[s][1] = sn[s][2] = 0.f; sd[s][0] = sd[s][1] = sd[s][2] = 0.f;
+            if (!is_real(s)) continue;
+            float gx = 0.f, gy = 0.f;
+            if (dok) {
+                float tx, ty;
+                project(w, L, X[s] + ray[s][0] * step, Y[s] + ray[s][1] * step, Z[s] + ray[s][2] * step, tx, ty);
+                gx = tx - qx[s]; gy = ty - qy[s];
+            }
+            const int left = (int)floorf(qx[s]), top = (int)floorf(qy[s]);
+            const float fx = qx[s] - (float)left, fy = qy[s] - (float)top;
+            const uint4 Q = __ldg(L.quad + (size_t)top * L.pitch + left);
+            float a[3], b[3], c[3], e[3];
+            a[0] = lutw[(Q.x & 0xFF) * LUT_REP]; a[1] = lutw[((Q.x >> 8) & 0xFF) * LUT_REP]; a[2] = lutw[((Q.x >> 16) & 0xFF) * LUT_REP];
+            b[0] = lutw[(Q.y & 0xFF) * LUT_REP]; b[1] = lutw[((Q.y >> 8) & 0xFF) * LUT_REP]; b[2] = lutw[((Q.y >> 16) & 0xFF) * LUT_REP];
+            c[0] = lutw[(Q.z & 0xFF) * LUT_REP]; c[1] = lutw[((Q.z >> 8) & 0xFF) * LUT_REP]; c[2] = lutw[((Q.z >> 16) & 0xFF) * LUT_REP];
+            e[0] = lutw[(Q.w & 0xFF) * LUT_REP]; e[1] = lutw[((Q.w >> 8) & 0xFF) * LUT_REP]; e[2] = lutw[((Q.w >> 16) & 0xFF) * LUT_REP];
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                const float x0 = (1.f - fx) * a[ch] + fx * b[ch];
+                const float x3 = (1.f - fx) * c[ch] + fx * e[ch];
+                sn[s][ch] = (1.f - fy) * x0 + fy * x3;
+                const float der = gx * (b[ch] - a[ch]) + gy * (c[ch] - a[ch]) + (gy * fx + gx * fy) * (a[ch] - b[ch] - c[ch] + e[ch]);
+                sd[s][ch] = dok ? der * dd : 0.f;        // deriv /= stepSize with stepSize = 1 / d (patch_sampler.cc:100,129-130)
+            }
+        }
         return dok ? 3u : 1u;
     }
 
@@ -402,8 +387,7 @@ struct Patch {
             int slot = k;
             if (candidates) { if (!((avail >> k) & 1u)) continue; }
             else slot = gbcast(sel_l, k);
-            float sn[3];
-            const unsigned r = sample(&views[job->gview[slot]], sn);
+            const unsigned r = sample(&views[job->gview[slot]]);
             const bool need_ncc = (candidates || want_ncc) && (r & 1u);
             float c0 = gbcast(cs0_l, k), c1 = gbcast(cs1_l, k), c2 = gbcast(cs2_l, k);
             const bool cs_now = !candidates && cs_active && (r & 1u);
@@ -414,79 +398,69 @@ struct Patch {
                 if (cs_active && !(r & 1u)) cs_active = false;
             }
             float ncc = -1.f;
-            float my0 = 0.f, my1 = 0.f, my2 = 0.f;
-            if (need_ncc) {                               // getFastNCC (patch_sampler.cc:143-162): means first
+            if (need_ncc) {                               // getFastNCC (patch_sampler.cc:143-162)
                 const float inv_n = 1.f / (float)NS;
-                my0 = gsum(sn[0]) * inv_n; my1 = gsum(sn[1]) * inv_n; my2 = gsum(sn[2]) * inv_n;
-            }
-            // second sweep over the lane's samples (from shared memory): NCC deviations, colour-scale sums, and the
-            // Gauss-Newton terms; when the colour scale is updated at this state the terms need the NEW scale, so they are
-            // formed in a repetition of the same loop
-#pragma unroll 1
-            for (int rep = 0; rep < 2; ++rep) {
-                const bool do_ncc = rep == 0 && need_ncc;
-                const bool do_cs = rep == 0 && cs_now;
-                const bool do_gn = !candidates && (r & 2u) && (rep == (cs_now ? 1 : 0));
-                if (!(do_ncc || do_cs || do_gn)) continue;
+                float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+#pragma unroll
+                for (int s = 0; s < SLOTS; ++s) { t0 += sn[s][0]; t1 += sn[s][1]; t2 += sn[s][2]; }
+                const float my0 = gsum(t0) * inv_n, my1 = gsum(t1) * inv_n, my2 = gsum(t2) * inv_n;
                 float sqrDevY = 0.f, devXY = 0.f;
-                float ab0 = 0.f, ab1 = 0.f, ab2 = 0.f, aa0 = 0.f, aa1 = 0.f, aa2 = 0.f;
-#pragma unroll 1
+#pragma unroll
                 for (int s = 0; s < SLOTS; ++s) {
                     if (!is_real(s)) continue;
-                    const float n0 = pw(PW_N + 3 * s), n1 = pw(PW_N + 3 * s + 1), n2 = pw(PW_N + 3 * s + 2);
-                    const float m0 = pw(PW_M + 3 * s), m1 = pw(PW_M + 3 * s + 1), m2 = pw(PW_M + 3 * s + 2);
-                    if (do_ncc) {
-                        const float y0 = n0 - my0, y1 = n1 - my1, y2 = n2 - my2;
-                        sqrDevY += y0 * y0 + y1 * y1 + y2 * y2;
-                        devXY += (m0 - mx0) * y0 + (m1 - mx1) * y1 + (m2 - mx2) * y2;
-                    }
-                    if (do_cs) {                          // patch_optimization.cc:95-101
-                        ab0 += (m0 - n0 * c0) * n0; ab1 += (m1 - n1 * c1) * n1; ab2 += (m2 - n2 * c2) * n2;
-                        aa0 += n0 * n0; aa1 += n1 * n1; aa2 += n2 * n2;
-                    }
-                    if (do_gn) {
-                        // Gauss-Newton terms (patch_optimization.cc:283-288 / :324-343); only meaningful when every view's
-                        // derivative path succeeded, which the caller checks through p_der_ok
-                        const float g0 = c0 * pw(PW_D + 3 * s), g1 = c1 * pw(PW_D + 3 * s + 1), g2 = c2 * pw(PW_D + 3 * s + 2);
-                        const float r0 = m0 - c0 * n0, r1 = m1 - c1 * n1, r2 = m2 - c2 * n2;
-                        num += g0 * r0 + g1 * r1 + g2 * r2;
-                        den += g0 * g0 + g1 * g1 + g2 * g2;
-                        if (want_normal) {
-                            const int ks = sample_index(s);
-                            const float fi = (float)(ks % 5 - 2), fj = (float)(ks / 5 - 2);
-                            const float gg[3] = {g0, g1, g2};
-                            const float rr[3] = {r0, r1, r2};
+                    const float y0 = sn[s][0] - my0, y1 = sn[s][1] - my1, y2 = sn[s][2] - my2;
+                    sqrDevY += y0 * y0 + y1 * y1 + y2 * y2;
+                    devXY += (mc[s][0] - mx0) * y0 + (mc[s][1] - mx1) * y1 + (mc[s][2] - mx2) * y2;
+                }
+                sqrDevY = gsum(sqrDevY); devXY = gsum(devXY);
+                const float p = sqrDevX * sqrDevY;          // devXY / sqrt(p), -1 when sqrt(p) is not > 0
+                ncc = p > 0.f ? devXY * rsqrt_fast(p) : -1.f;
+            }
+            if (cs_now) {                                 // computeColorScale for this view (patch_optimization.cc:88-110)
+                float ab0 = 0.f, ab1 = 0.f, ab2 = 0.f, aa0 = 0.f, aa1 = 0.f, aa2 = 0.f;
 #pragma unroll
-                            for (int ch = 0; ch < 3; ++ch) {
-                                const float a0 = gg[ch];
-                                const float a1 = fi * a0;      // (ii * cs) * deriv == ii * (cs * deriv) exactly for ii in {-2..2}
-                                const float a2 = fj * a0;
-                                A0 += a0 * a0; A1 += a0 * a1; A2 += a0 * a2;
-                                A3 += a1 * a1; A4 += a1 * a2; A5 += a2 * a2;
-                                B0 += a0 * rr[ch]; B1 += a1 * rr[ch]; B2 += a2 * rr[ch];
-                            }
+                for (int s = 0; s < SLOTS; ++s) {
+                    if (!is_real(s)) continue;
+                    ab0 += (mc[s][0] - sn[s][0] * c0) * sn[s][0]; ab1 += (mc[s][1] - sn[s][1] * c1) * sn[s][1]; ab2 += (mc[s][2] - sn[s][2] * c2) * sn[s][2];
+                    aa0 += sn[s][0] * sn[s][0]; aa1 += sn[s][1] * sn[s][1]; aa2 += sn[s][2] * sn[s][2];
+                }
+                float cc[3] = {c0, c1, c2};
+                const float ab[3] = {gsum(ab0), gsum(ab1), gsum(ab2)};
+                const float aa[3] = {gsum(aa0), gsum(aa1), gsum(aa2)};
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) {
+                    if ((double)fabsf(aa[ch]) > 1e-6) {
+                        cc[ch] += ab[ch] * rcp_fast(aa[ch]);
+                        if ((double)cc[ch] > 1e3) opti = false;
+                    } else
+                        opti = false;
+                }
+                c0 = cc[0]; c1 = cc[1]; c2 = cc[2];
+                if (gl == k) { cs0_l = c0; cs1_l = c1; cs2_l = c2; }
+            }
+            // Gauss-Newton terms (patch_optimization.cc:283-288 / :324-343) with the colour scale of THIS state; only
+            // meaningful when every view's derivative path succeeded, which the caller checks through p_der_ok
+            if (!candidates && (r & 2u)) {
+#pragma unroll
+                for (int s = 0; s < SLOTS; ++s) {
+                    if (!is_real(s)) continue;
+                    const float g0 = c0 * sd[s][0], g1 = c1 * sd[s][1], g2 = c2 * sd[s][2];
+                    const float r0 = mc[s][0] - c0 * sn[s][0], r1 = mc[s][1] - c1 * sn[s][1], r2 = mc[s][2] - c2 * sn[s][2];
+                    num += g0 * r0 + g1 * r1 + g2 * r2;
+                    den += g0 * g0 + g1 * g1 + g2 * g2;
+                    if (want_normal) {
+                        const float gg[3] = {g0, g1, g2};
+                        const float rr[3] = {r0, r1, r2};
+#pragma unroll
+                        for (int ch = 0; ch < 3; ++ch) {
+                            const float a0 = gg[ch];
+                            const float a1 = fi[s] * a0;      // (ii * cs) * deriv == ii * (cs * deriv) exactly for ii in {-2..2}
+                            const float a2 = fj[s] * a0;
+                            A0 += a0 * a0; A1 += a0 * a1; A2 += a0 * a2;
+                            A3 += a1 * a1; A4 += a1 * a2; A5 += a2 * a2;
+                            B0 += a0 * rr[ch]; B1 += a1 * rr[ch]; B2 += a2 * rr[ch];
                         }
                     }
-                }
-                if (do_ncc) {
-                    sqrDevY = gsum(sqrDevY); devXY = gsum(devXY);
-                    const float p = sqrDevX * sqrDevY;          // devXY / sqrt(p), -1 when sqrt(p) is not > 0
-                    ncc = p > 0.f ? devXY * rsqrt_fast(p) : -1.f;
-                }
-                if (do_cs) {
-                    float cc[3] = {c0, c1, c2};
-                    const float ab[3] = {gsum(ab0), gsum(ab1), gsum(ab2)};
-                    const float aa[3] = {gsum(aa0), gsum(aa1), gsum(aa2)};
-#pragma unroll
-                    for (int ch = 0; ch < 3; ++ch) {
-                        if ((double)fabsf(aa[ch]) > 1e-6) {
-                            cc[ch] += ab[ch] * rcp_fast(aa[ch]);
-                            if ((double)cc[ch] > 1e3) opti = false;
-                        } else
-                            opti = false;
-                    }
-                    c0 = cc[0]; c1 = cc[1]; c2 = cc[2];
-                    if (gl == k) { cs0_l = c0; cs1_l = c1; cs2_l = c2; }
                 }
             }
             if (candidates) {
@@ -786,15 +760,12 @@ struct Patch {
         float q1x, q1y, q1z, q2x, q2y, q2z, q3x, q3y, q3z;
         {
             const float c0x = __ldg(&rv->campos[0]), c0y = __ldg(&rv->campos[1]), c0z = __ldg(&rv->campos[2]);
-            int k = sample_index(1);
-            float t = depth + (float)(k % 5 - 2) * dzI + (float)(k / 5 - 2) * dzJ;
-            q1x = c0x + t * pw(PW_RAY + 3); q1y = c0y + t * pw(PW_RAY + 4); q1z = c0z + t * pw(PW_RAY + 5);
-            k = sample_index(2);
-            t = depth + (float)(k % 5 - 2) * dzI + (float)(k / 5 - 2) * dzJ;
-            q2x = c0x + t * pw(PW_RAY + 6); q2y = c0y + t * pw(PW_RAY + 7); q2z = c0z + t * pw(PW_RAY + 8);
-            k = sample_index(3);
-            t = depth + (float)(k % 5 - 2) * dzI + (float)(k / 5 - 2) * dzJ;
-            q3x = c0x + t * pw(PW_RAY + 9); q3y = c0y + t * pw(PW_RAY + 10); q3z = c0z + t * pw(PW_RAY + 11);
+            float t = depth + fi[1] * dzI + fj[1] * dzJ;
+            q1x = c0x + t * ray[1][0]; q1y = c0y + t * ray[1][1]; q1z = c0z + t * ray[1][2];
+            t = depth + fi[2] * dzI + fj[2] * dzJ;
+            q2x = c0x + t * ray[2][0]; q2y = c0y + t * ray[2][1]; q2z = c0z + t * ray[2][2];
+            t = depth + fi[3] * dzI + fj[3] * dzJ;
+            q3x = c0x + t * ray[3][0]; q3y = c0y + t * ray[3][1]; q3z = c0z + t * ray[3][2];
         }
         const float ax_ = gbcast(q2x, 6) - gbcast(q2x, 2);
         const float ay_ = gbcast(q2y, 6) - gbcast(q2y, 2);
@@ -811,19 +782,23 @@ struct Patch {
     }
 };
 
-// Binds a thread to its group and its shared-memory columns.  lut_rep: LUT_REP-fold replicated table
-// (lut_rep[v * LUT_REP + r] = srgb2lin[v]), priv_base: PRIV_WORDS * TPB floats of the block, tid: thread index in the block.
-template <int TPB>
-__device__ __forceinline__ void bind_thread(Patch<TPB>& p, const DevSettings* st, const ViewParams* views,
-                                            const float* lut_rep, float* priv_base, int tid)
+// Binds a thread to its group.  lut_rep: LUT_REP-fold replicated table in shared memory (lut_rep[v * LUT_REP + r] = srgb2lin[v]),
+// tid: thread index in the block.
+__device__ __forceinline__ void bind_thread(Patch& p, const DevSettings* st, const ViewParams* views, const float* lut_rep, int tid)
 {
     const int lane = tid & 31;
     p.st = st; p.views = views;
     p.lutw = lut_rep + (lane & (LUT_REP - 1));
-    p.priv = priv_base + tid;
     p.gl = lane & (GROUP - 1);
     p.gmask = ((1u << GROUP) - 1u) << (lane & ~(GROUP - 1));
-    p.stage = Patch<TPB>::DONE;
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) {
+        const int k = p.sample_index(s);
+        const bool real = p.is_real(s);
+        p.fi[s] = real ? (float)(k % 5 - 2) : 0.f;
+        p.fj[s] = real ? (float)(k / 5 - 2) : 0.f;
+    }
+    p.stage = Patch::DONE;
     p.n_sets = 0u;
 }
 

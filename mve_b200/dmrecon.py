@@ -76,7 +76,8 @@ PATCH_OUT = np.dtype([("conf", "<f4"), ("depth", "<f4"), ("dz_i", "<f4"), ("dz_j
 
 EXPORTS = ["b200mvs_default_settings", "b200mvs_create", "b200mvs_destroy", "b200mvs_last_error", "b200mvs_version",
            "b200mvs_upload_view", "b200mvs_upload_view_device", "b200mvs_set_view_camera", "b200mvs_set_features", "b200mvs_num_levels",
-           "b200mvs_get_level", "b200mvs_global_view_selection", "b200mvs_optimize_patches", "b200mvs_reconstruct"]
+           "b200mvs_get_level", "b200mvs_global_view_selection", "b200mvs_optimize_patches", "b200mvs_reconstruct",
+           "b200mvs_plan_views"]
 
 
 def lib():
@@ -107,6 +108,7 @@ def lib():
                                            C.c_void_p, C.c_void_p]
     L.b200mvs_reconstruct.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p]
+    L.b200mvs_plan_views.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     _LIB = L
     return L
 
@@ -204,6 +206,12 @@ class Scene:
         out = np.empty(64, np.int32)
         n = self._check(self._lib.b200mvs_global_view_selection(self._h, C.byref(settings), ref_view, _p(out), 64))
         return out[:n].tolist()
+
+    def plan_views(self, settings: Settings, ref_views: Sequence[int]):
+        """Global view selection + seed lists of these reference views ahead of their reconstruct() call; safe to call from
+        another thread while a reconstruct() of a previous batch is running (ctypes releases the GIL)."""
+        refs = np.asarray(ref_views, np.int32)
+        self._check(self._lib.b200mvs_plan_views(self._h, C.byref(settings), len(refs), _p(refs)))
 
     def optimize_patches(self, settings: Settings, ref_view: int, global_ids: Sequence[int], patches: np.ndarray,
                          stats: Optional[Stats] = None) -> np.ndarray:

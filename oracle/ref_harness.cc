@@ -11,12 +11,14 @@
  *       dmrecon.cc:293-296 / :374-377) per record of IN.bin and writes the results to OUT.bin.
  *       Record layouts = mvs_oracle_patch_in / mvs_oracle_patch_out of oracle/mvs_oracle.h.
  *
- *   ref_harness timed SCENE SCALE NRN SECONDS VIEW [VIEW...]
- *       CPU baseline: runs mvs::DMRecon(scene, settings).start() for the listed views, one thread per view
- *       (the reference's own parallelism, apps/dmrecon/dmrecon.cc:285), sets Progress::cancelled after
- *       SECONDS (the reference's cooperative cancel, dmrecon.cc:353) and prints one JSON line with the
- *       filled pixel counts and the elapsed time.  SECONDS <= 0 runs to completion.
+ *   ref_harness timed SCENE SCALE NRN SECONDS STEPS VIEW [VIEW...]
+ *       CPU baseline: STEPS times, runs mvs::DMRecon(scene, settings).start() for the listed views, one thread per view
+ *       (the reference's own parallelism, apps/dmrecon/dmrecon.cc:285); the clock starts when every view has reached
+ *       processQueue (Progress::status == RECON_QUEUE), Progress::cancelled is set SECONDS later (the reference's
+ *       cooperative cancel, dmrecon.cc:353); prints one JSON line per step with the pixels filled inside the clocked
+ *       interval and its length.  SECONDS <= 0 runs to completion.
  */
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <cstdint>
@@ -117,69 +119,94 @@ static int run_patches(int argc, char** argv)
 
 static int run_timed(int argc, char** argv)
 {
-    if (argc < 7) { std::fprintf(stderr, "usage: ref_harness timed SCENE SCALE NRN SECONDS VIEW...\n"); return 2; }
+    if (argc < 8) { std::fprintf(stderr, "usage: ref_harness timed SCENE SCALE NRN SECONDS STEPS VIEW...\n"); return 2; }
     mve::Scene::Ptr scene = mve::Scene::create(argv[2]);
     const int scale = std::atoi(argv[3]);
     const int nrn = std::atoi(argv[4]);
     const double seconds = std::atof(argv[5]);
+    const int steps = std::max(1, std::atoi(argv[6]));
     std::vector<int> ids;
-    for (int i = 6; i < argc; ++i) ids.push_back(std::atoi(argv[i]));
+    for (int i = 7; i < argc; ++i) ids.push_back(std::atoi(argv[i]));
     scene->get_bundle();
-    /* touch the input images first so that the timed part is reconstruction, not file I/O */
+    /* touch the input images first so that no step measures file I/O */
     for (int id : ids) scene->get_views()[id]->get_byte_image("undistorted");
-    std::vector<mvs::DMRecon*> recons(ids.size(), nullptr);
-    std::vector<std::size_t> filled(ids.size(), 0);
-    std::vector<int> done(ids.size(), 0);
-    std::atomic<int> running((int)ids.size());
-    std::mutex mtx;
-    auto t0 = std::chrono::steady_clock::now();
-    std::vector<std::thread> th;
-    for (std::size_t k = 0; k < ids.size(); ++k) {
-        th.emplace_back([&, k]() {
-            try {
-                mvs::Settings settings;
-                settings.refViewNr = ids[k];
-                settings.scale = scale;
-                settings.nrReconNeighbors = nrn;
-                settings.quiet = true;
-                settings.keepDzMap = true;
-                settings.keepConfidenceMap = true;
-                mvs::DMRecon recon(scene, settings);
-                { std::lock_guard<std::mutex> lk(mtx); recons[k] = &recon; }
-                recon.start();
-                std::lock_guard<std::mutex> lk(mtx);
-                filled[k] = recon.getProgress().filled;
-                done[k] = recon.getProgress().cancelled ? 0 : 1;
-                recons[k] = nullptr;
-            } catch (std::exception& e) {
-                std::fprintf(stderr, "view %d failed: %s\n", ids[k], e.what());
-                std::lock_guard<std::mutex> lk(mtx);
-                recons[k] = nullptr;
-            }
-            running--;
-        });
-    }
-    if (seconds > 0) {
-        while (running.load() > 0) {
-            std::this_thread::sleep_for(std::chrono::milliseconds(20));
-            double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-            if (el >= seconds) {
-                std::lock_guard<std::mutex> lk(mtx);
-                for (std::size_t k = 0; k < ids.size(); ++k) {
-                    mvs::DMRecon* r = recons[k];
-                    if (r) r->getProgress().cancelled = true;
+    for (int step = 0; step < steps; ++step) {
+        std::vector<mvs::DMRecon*> recons(ids.size(), nullptr);
+        std::vector<std::size_t> filled(ids.size(), 0);
+        std::vector<int> state(ids.size(), 0);       /* 0 setting up, 1 running, 2 finished, 3 failed */
+        std::vector<int> done(ids.size(), 0);
+        std::atomic<int> running((int)ids.size());
+        std::mutex mtx;
+        std::vector<std::thread> th;
+        for (std::size_t k = 0; k < ids.size(); ++k) {
+            th.emplace_back([&, k]() {
+                try {
+                    mvs::Settings settings;
+                    settings.refViewNr = ids[k];
+                    settings.scale = scale;
+                    settings.nrReconNeighbors = nrn;
+                    settings.quiet = true;
+                    settings.keepDzMap = true;
+                    settings.keepConfidenceMap = true;
+                    mvs::DMRecon recon(scene, settings);
+                    { std::lock_guard<std::mutex> lk(mtx); recons[k] = &recon; state[k] = 1; }
+                    recon.start();
+                    std::lock_guard<std::mutex> lk(mtx);
+                    filled[k] = recon.getProgress().filled;
+                    done[k] = recon.getProgress().cancelled ? 0 : 1;
+                    recons[k] = nullptr;
+                    state[k] = 2;
+                } catch (std::exception& e) {
+                    std::fprintf(stderr, "view %d failed: %s\n", ids[k], e.what());
+                    std::lock_guard<std::mutex> lk(mtx);
+                    recons[k] = nullptr;
+                    state[k] = 3;
                 }
+                running--;
+            });
+        }
+        /* The clock starts when EVERY view has reached processQueue (RECON_QUEUE): SingleView creation, image pyramids
+         * (serialised by the reference's global ImagePyramidCache mutex, image_pyramid.cc:102,137), global view selection
+         * and the seed features are set-up, not the region growing this metric is about. */
+        auto sum_filled = [&]() {
+            std::size_t t = 0;
+            for (std::size_t k = 0; k < ids.size(); ++k) t += recons[k] ? recons[k]->getProgress().filled : filled[k];
+            return t;
+        };
+        std::size_t filled0 = 0;
+        auto t_setup = std::chrono::steady_clock::now();
+        for (;;) {
+            std::this_thread::sleep_for(std::chrono::milliseconds(5));
+            std::lock_guard<std::mutex> lk(mtx);
+            bool all = true;
+            for (std::size_t k = 0; k < ids.size(); ++k) {
+                if (state[k] == 0) all = false;
+                else if (state[k] == 1 && recons[k] && recons[k]->getProgress().status < mvs::RECON_QUEUE) all = false;
+            }
+            if (all) { filled0 = sum_filled(); break; }
+        }
+        auto t0 = std::chrono::steady_clock::now();
+        const double setup_s = std::chrono::duration<double>(t0 - t_setup).count();
+        std::size_t filled1 = 0;
+        for (;;) {
+            std::this_thread::sleep_for(std::chrono::milliseconds(5));
+            const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            if ((seconds > 0 && el >= seconds) || running.load() == 0) {
+                std::lock_guard<std::mutex> lk(mtx);
+                filled1 = sum_filled();
+                for (std::size_t k = 0; k < ids.size(); ++k) if (recons[k]) recons[k]->getProgress().cancelled = true;
                 break;
             }
         }
+        const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        for (auto& t : th) t.join();
+        int complete = 0;
+        for (std::size_t k = 0; k < ids.size(); ++k) complete += done[k];
+        std::printf("{\"filled\": %zu, \"seconds\": %.6f, \"views\": %zu, \"views_completed\": %d, \"threads\": %zu, "
+                    "\"filled_before_clock\": %zu, \"setup_seconds\": %.3f}\n",
+                    filled1 - filled0, el, ids.size(), complete, ids.size(), filled0, setup_s);
+        std::fflush(stdout);
     }
-    for (auto& t : th) t.join();
-    double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-    std::size_t total = 0;
-    int complete = 0;
-    for (std::size_t k = 0; k < ids.size(); ++k) { total += filled[k]; complete += done[k]; }
-    std::printf("{\"filled\": %zu, \"seconds\": %.6f, \"views\": %zu, \"views_completed\": %d, \"threads\": %zu}\n",
-                total, el, ids.size(), complete, ids.size());
     return 0;
 }
 

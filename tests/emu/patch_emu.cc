@@ -74,13 +74,11 @@ int emu_optimize_patches(const EmuView* views, int n_views, int ref_view, int W,
     job.ref_pitch = views[ref_view].pitch[st.scale];
 
     /* one warp = four 8-lane groups; each group takes patches through a ticket counter exactly like the kernels'
-     * optimise_entries() (mve_b200/csrc/b200mvs.cu); "shared memory" = the replicated table + one column per lane */
+     * optimise_entries() (mve_b200/csrc/b200mvs.cu); "shared memory" = the replicated table */
     simt_emu::Warp warp;
     for (int g = 0; g < 4; ++g) warp.sub8[g].bar.n = 8;
     std::vector<float> lut_rep(256 * LUT_REP);
     for (int i = 0; i < 256 * LUT_REP; ++i) lut_rep[i] = lut[i / LUT_REP];
-    constexpr int TPB = 32;
-    std::vector<float> priv(PRIV_WORDS * TPB, 0.f);
     std::atomic<int> ticket(0);
     std::vector<std::thread> lanes;
     for (int lane = 0; lane < 32; ++lane) {
@@ -89,8 +87,8 @@ int emu_optimize_patches(const EmuView* views, int n_views, int ref_view, int W,
             simt_emu::t_lane = lane;
             simt_emu::t_sense_full = 0;
             simt_emu::t_sense_sub = 0;
-            Patch<TPB> p;
-            bind_thread(p, &st, vp.data(), lut_rep.data(), priv.data(), lane);
+            Patch p;
+            bind_thread(p, &st, vp.data(), lut_rep.data(), lane);
             bool have = false;
             int idx = 0;
             unsigned sets_before = 0;
