@@ -68,8 +68,10 @@ void b200mvs_default_settings(b200mvs_settings* s);
  * (fancy_progress_printer.cc:84-91, apps/umve/viewinspect/imageoperations.cc:177-184). */
 typedef struct b200mvs_progress {
     volatile int32_t  status;     /* ReconStatus: 0 idle, 1 globalvs, 2 features, 3 queue, 4 saving, 5 cancelled */
-    volatile int32_t  cancelled;  /* set from outside (any thread) to cancel; relayed to the running kernel within ~0.2 ms,
-                                     honoured at the next frontier round; any view's flag stops the whole batch */
+    volatile int32_t  cancelled;  /* set from outside (any thread) to cancel THIS view; relayed to the running kernel within
+                                     ~0.2 ms, its queue is dropped at the next frontier round, status ends as 5 and its maps
+                                     are not written; the other views of the batch go on.  The call returns
+                                     B200MVS_ERR_CANCELLED only when every view of the batch was cancelled */
     volatile uint64_t filled;
     volatile uint64_t queue_size;
     volatile uint64_t start_time;

@@ -86,12 +86,11 @@ struct FrontierCtl {                            // device memory, zeroed before 
     int pad;
 };
 
-struct HostMirror {                             // mapped pinned host memory
-    volatile int cancel;                        // host -> device
+struct HostMirror {                             // mapped pinned host memory; followed by filled[n_jobs] (device -> host)
+    volatile int cancel;                        // host -> device: stop the whole batch at the next round
     volatile int pad;
     volatile unsigned long long round, queue;   // device -> host
-    volatile unsigned long long filled[1];      // [n_jobs]
-};
+};                                              // ... and by cancel_job[n_jobs] (host -> device: drop this view's queue)
 
 template <typename T> struct DevBuf {
     T* p = nullptr;
@@ -132,6 +131,7 @@ struct b200mvs_ctx {
     DevBuf<FrontierCtl> ctl;
     DevBuf<unsigned> hist;
     DevBuf<int> thr_bin;
+    DevBuf<int> job_cancel;
     int frontier_grid = 0;             // CTAs of the cooperative launch (= what fits on the chip)
     int optimize_grid = 0;             // resident CTAs of k_optimize
     unsigned long long* h_counters = nullptr;   // pinned
@@ -558,6 +558,9 @@ struct FrontierParams {
     unsigned* hist;                             // [n_jobs][HIST_PER_JOB], zero on entry (only with a threshold)
     int* thr_bin;                               // [n_jobs]
     HostMirror* host;
+    volatile unsigned long long* host_filled;   // [n_jobs], mapped
+    volatile int* host_cancel_job;              // [n_jobs], mapped
+    int* job_cancel;                            // [n_jobs], device copy refreshed every round
     int band_bins;                              // frontier_band in fine bins (0 = off)
     int topk;                                   // frontier_topk (0 = off)
 };
@@ -705,7 +708,10 @@ k_frontier(const FrontierParams P)
         Entry* const cur = P.list[p];
         if (blockIdx.x == 0) {                                  // progress out (dmrecon.cc:355-364)
             if (threadIdx.x == 0) { P.host->round = ctl->rounds; P.host->queue = n_cur; }
-            for (int j = threadIdx.x; j < P.n_jobs; j += blockDim.x) P.host->filled[j] = __ldcg(&filled[j]);
+            for (int j = threadIdx.x; j < P.n_jobs; j += blockDim.x) {
+                P.host_filled[j] = __ldcg(&filled[j]);
+                if (P.host_cancel_job[j]) P.job_cancel[j] = 1;   // this view's entries are dropped from now on (Progress::cancelled)
+            }
         }
         // A: stale test (dmrecon.cc:371-373); without a threshold the per-pixel bid follows immediately
         for (size_t i = gtid; i < n_cur; i += gthreads) {
@@ -713,7 +719,7 @@ k_frontier(const FrontierParams P)
             const int j = e.jobdir & 0xFFFFFF;
             const JobParams& J = P.jobs[j];
             const int idx = ((e.xy >> 16) & 0xFFFF) * J.W + (e.xy & 0xFFFF);
-            if (__ldcg(&J.conf[idx]) > e.conf) { cur[i].jobdir = -1; continue; }
+            if (__ldcg(&J.conf[idx]) > e.conf || __ldcg(&P.job_cancel[j])) { cur[i].jobdir = -1; continue; }
             if (!thresholded) atomicMax(&J.sel[idx], entry_key(e));
             else {
                 const int b = conf_bin(e.conf);
@@ -852,7 +858,7 @@ k_frontier(const FrontierParams P)
     if (lead) ctl->barriers = n_bar;
     if (blockIdx.x == 0) {
         if (threadIdx.x == 0) { P.host->round = ctl->rounds; P.host->queue = 0ull; }
-        for (int j = threadIdx.x; j < P.n_jobs; j += blockDim.x) P.host->filled[j] = __ldcg(&filled[j]);
+        for (int j = threadIdx.x; j < P.n_jobs; j += blockDim.x) P.host_filled[j] = __ldcg(&filled[j]);
     }
 #undef PHASE_END
 }
@@ -1092,7 +1098,7 @@ int b200mvs_create(int device, int n_views, b200mvs_ctx** out)
     if ((e = cudaMalloc(&ctx->d_views, sizeof(ViewParams) * n_views)) != cudaSuccess) return bail("cudaMalloc(views)", e);
     if ((e = cudaMalloc(&ctx->d_lut, 256 * sizeof(float))) != cudaSuccess) return bail("cudaMalloc(lut)", e);
     if ((e = cudaMallocHost(&ctx->h_counters, sizeof(unsigned long long) * 4096)) != cudaSuccess) return bail("cudaMallocHost", e);
-    if ((e = cudaHostAlloc(&ctx->h_mirror, sizeof(unsigned long long) * 4200, cudaHostAllocMapped)) != cudaSuccess) return bail("cudaHostAlloc", e);
+    if ((e = cudaHostAlloc(&ctx->h_mirror, sizeof(unsigned long long) * 8192, cudaHostAllocMapped)) != cudaSuccess) return bail("cudaHostAlloc", e);
     // sRGB code value -> linear: the formula documented at mvs_tools.cc:21-29; tests/test_oracle_vs_reference.py::test_srgb_table_matches_reference checks the
     // 256 floats against the reference table.
     float lut[256];
@@ -1122,7 +1128,7 @@ void b200mvs_destroy(b200mvs_ctx* ctx)
     }
     ctx->ent_a.release(); ctx->ent_b.release(); ctx->run_in.release(); ctx->run_out.release(); ctx->written.release();
     ctx->counters.release(); ctx->d_jobs.release(); ctx->d_settings.release(); ctx->maps.release();
-    ctx->ctl.release(); ctx->hist.release(); ctx->thr_bin.release();
+    ctx->ctl.release(); ctx->hist.release(); ctx->thr_bin.release(); ctx->job_cancel.release();
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -1499,6 +1505,7 @@ int b200mvs_reconstruct(b200mvs_ctx* ctx, const b200mvs_settings* s, int n_refs,
     CK(ctx->d_settings.reserve(1));
     CK(ctx->ctl.reserve(1));
     CK(ctx->thr_bin.reserve(n_refs));
+    CK(ctx->job_cancel.reserve(n_refs));
     if (thresholded) CK(ctx->hist.reserve((size_t)n_refs * HIST_PER_JOB));
     if ((size_t)(C_NUM + n_refs) > 4096) return fail(ctx, B200MVS_ERR_INVALID_ARG, "too many reference views in one batch");
     const DevSettings ds = to_dev(*s);
@@ -1509,7 +1516,10 @@ int b200mvs_reconstruct(b200mvs_ctx* ctx, const b200mvs_settings* s, int n_refs,
     if (thresholded) CK(cudaMemsetAsync(ctx->hist.p, 0, sizeof(unsigned) * (size_t)n_refs * HIST_PER_JOB, st));
     if (!seeds.empty()) CK(cudaMemcpyAsync(ctx->run_in.p, seeds.data(), sizeof(Entry) * seeds.size(), cudaMemcpyHostToDevice, st));
     HostMirror* mirror = reinterpret_cast<HostMirror*>(ctx->h_mirror);
-    std::memset(ctx->h_mirror, 0, sizeof(HostMirror) + sizeof(unsigned long long) * n_refs);
+    std::memset(ctx->h_mirror, 0, sizeof(HostMirror) + (sizeof(unsigned long long) + sizeof(int)) * n_refs);
+    volatile unsigned long long* m_filled = reinterpret_cast<volatile unsigned long long*>(mirror + 1);
+    volatile int* m_cancel_job = reinterpret_cast<volatile int*>(m_filled + n_refs);
+    CK(cudaMemsetAsync(ctx->job_cancel.p, 0, sizeof(int) * n_refs, st));
 
     FrontierParams P;
     P.list[0] = ctx->ent_a.p; P.list[1] = ctx->ent_b.p;
@@ -1517,16 +1527,21 @@ int b200mvs_reconstruct(b200mvs_ctx* ctx, const b200mvs_settings* s, int n_refs,
     P.cap = cap; P.n_seeds = (int)seeds.size(); P.n_jobs = n_refs;
     P.st = ctx->d_settings.p; P.jobs = ctx->d_jobs.p; P.views = ctx->d_views; P.lut = ctx->d_lut;
     P.counters = ctx->counters.p; P.ctl = ctx->ctl.p; P.hist = ctx->hist.p; P.thr_bin = ctx->thr_bin.p;
-    P.host = mirror;
+    P.host = mirror; P.host_filled = m_filled; P.host_cancel_job = m_cancel_job; P.job_cancel = ctx->job_cancel.p;
     P.band_bins = s->frontier_band > 0.f ? std::max(1, (int)(s->frontier_band * (float)HIST_FINE)) : 0;
     P.topk = (int)std::min<uint32_t>(s->frontier_topk, 1u << 30);
 
-    if (progress)                      // `if (progress.cancelled) return` at the head of every stage (dmrecon.cc:100-104,336)
-        for (int j = 0; j < n_refs; ++j)
-            if (progress[j].cancelled) {
-                for (int k = 0; k < n_refs; ++k) progress[k].status = 5;
-                return fail(ctx, B200MVS_ERR_CANCELLED, "reconstruction cancelled");
-            }
+    // `if (progress.cancelled) return` at the head of every stage (dmrecon.cc:100-104,336): views cancelled before the launch
+    // never start; when every view is cancelled nothing runs at all
+    std::vector<char> job_cancelled(n_refs, 0);
+    if (progress) {
+        int n_c = 0;
+        for (int j = 0; j < n_refs; ++j) if (progress[j].cancelled) { job_cancelled[j] = 1; m_cancel_job[j] = 1; ++n_c; }
+        if (n_c == n_refs) {
+            for (int k = 0; k < n_refs; ++k) progress[k].status = 5;
+            return fail(ctx, B200MVS_ERR_CANCELLED, "reconstruction cancelled");
+        }
+    }
     // ---- one cooperative launch: seeds + all frontier rounds (DESIGN.md "Frontier schedule") ----
     if ((rc = prepare_kernels(ctx))) return rc;
     cudaEvent_t ev_begin = get_event(ctx, 0), ev_end = get_event(ctx, 1);
@@ -1542,24 +1557,29 @@ int b200mvs_reconstruct(b200mvs_ctx* ctx, const b200mvs_settings* s, int n_refs,
     cudaEvent_t ev_copied = get_event(ctx, 2);
     CK(cudaEventRecord(ev_copied, st));
     // While the kernel runs the host only relays: progress out (Progress::filled / queueSize, fancy_progress_printer.cc:84-91)
-    // and a cancel request in (imageoperations.cc:177-184) - any view's flag stops the batch at the next round.
+    // and cancel requests in (imageoperations.cc:177-184): a cancelled view's queue is dropped at the next round, the other
+    // views of the batch go on; when every view is cancelled the kernel stops.
     if (progress) {
         for (;;) {
             const cudaError_t q = cudaEventQuery(ev_copied);
             if (q == cudaSuccess) break;
             if (q != cudaErrorNotReady) return fail(ctx, B200MVS_ERR_CUDA, "frontier kernel: %s", cudaGetErrorString(q));
             const unsigned long long qs = mirror->queue;
+            int n_c = 0;
             for (int j = 0; j < n_refs; ++j) {
+                if (progress[j].cancelled) { job_cancelled[j] = 1; m_cancel_job[j] = 1; }
+                if (job_cancelled[j]) { ++n_c; continue; }
                 progress[j].status = 3;
-                progress[j].filled = mirror->filled[j];
+                progress[j].filled = m_filled[j];
                 progress[j].queue_size = qs;
-                if (progress[j].cancelled) mirror->cancel = 1;
             }
+            if (n_c == n_refs) mirror->cancel = 1;
             std::this_thread::sleep_for(std::chrono::microseconds(200));
         }
     }
     CK(cudaStreamSynchronize(st));
-    const bool cancelled = h_ctl->stop == ST_CANCELLED;
+    if (progress) for (int j = 0; j < n_refs; ++j) if (progress[j].cancelled) job_cancelled[j] = 1;
+    const bool cancelled = h_ctl->stop == ST_CANCELLED || std::all_of(job_cancelled.begin(), job_cancelled.end(), [](char c) { return c != 0; });
     if (ctx->h_counters[C_OVERFLOW] || h_ctl->stop == ST_OVERFLOW)
         return fail(ctx, B200MVS_ERR_OVERFLOW, "frontier buffer overflow (capacity %zu entries)", cap);
     if (stats) stats->n_seeds_success = ctx->h_counters[C_SEED_OK];
@@ -1570,6 +1590,7 @@ int b200mvs_reconstruct(b200mvs_ctx* ctx, const b200mvs_settings* s, int n_refs,
         for (int j = 0; j < n_refs; ++j) {
             const size_t np = (size_t)jobs[j].W * jobs[j].H;
             maps[j].width = jobs[j].W; maps[j].height = jobs[j].H;
+            if (job_cancelled[j]) continue;                  // RECON_CANCELLED: nothing is saved (dmrecon.cc:100-104)
             if (progress) progress[j].status = 4;
             if (maps[j].depth) CK(cudaMemcpyAsync(maps[j].depth, jobs[j].depth, np * 4, cudaMemcpyDeviceToHost, st));
             if (maps[j].conf) CK(cudaMemcpyAsync(maps[j].conf, jobs[j].conf, np * 4, cudaMemcpyDeviceToHost, st));
@@ -1592,7 +1613,7 @@ int b200mvs_reconstruct(b200mvs_ctx* ctx, const b200mvs_settings* s, int n_refs,
     uint64_t filled = 0;
     for (int j = 0; j < n_refs; ++j) {
         filled += ctx->h_counters[C_NUM + j];
-        if (progress) { progress[j].filled = ctx->h_counters[C_NUM + j]; progress[j].queue_size = 0; progress[j].status = cancelled ? 5 : 0; }
+        if (progress) { progress[j].filled = ctx->h_counters[C_NUM + j]; progress[j].queue_size = 0; progress[j].status = (cancelled || job_cancelled[j]) ? 5 : 0; }
     }
     if (stats) {
         stats->n_opt = ctx->h_counters[C_OPTS];

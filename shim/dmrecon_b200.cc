@@ -11,8 +11,10 @@
 //   start (dmrecon.cc:90-172)  views + bundle -> b200mvs context (cached per scene like ImagePyramidCache,
 //                              image_pyramid.cc:99-132), b200mvs_reconstruct, results attached with View::set_image
 //                              under the reference's embedding names (depth-L<s>, dz-L<s>, conf-L<s>, undist-L<s>),
-//                              same log lines, Progress kept up to date, cancellation -> RECON_CANCELLED
+//                              writePlyFile / plyPath through the reference's own save_ply_view, same log lines, Progress
+//                              updated live while the kernel runs, cancellation of a running view -> RECON_CANCELLED
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstring>
 #include <ctime>
@@ -21,12 +23,15 @@
 #include <memory>
 #include <mutex>
 #include <stdexcept>
+#include <thread>
 #include <vector>
 
 #include "dmrecon/dmrecon.h"
 #include "dmrecon/settings.h"
 #include "mve/image.h"
 #include "mve/image_tools.h"
+#include "mve/mesh_io_ply.h"
+#include "util/file_system.h"
 #include "util/string_utils.h"
 
 #include "b200mvs.h"
@@ -38,15 +43,20 @@ namespace {
 //
 // The reference driver runs DMRecon::start() concurrently from OpenMP threads (apps/dmrecon/dmrecon.cc:285).  Here the
 // concurrent calls are (i) spread round-robin over the GPUs named by B200MVS_DEVICES (default: device B200MVS_DEVICE or
-// 0) and (ii) per GPU COMBINED: one caller becomes the leader and submits every request that is waiting as ONE batched
-// b200mvs_reconstruct (all views of a batch advance together, which is what keeps the GPU full), the others sleep until
-// their result is there.
+// 0) and (ii) per GPU COMBINED: every caller only ENQUEUES its request; one of them becomes the leader, waits a short
+// collection window for the other threads of the OpenMP team to arrive, then does for the whole batch what each DMRecon
+// does for itself in the reference - global view selection, loading the colour images that are needed (once per view
+// and context) - and submits ONE b200mvs_reconstruct in which all views advance together.  While the kernel runs a
+// relay thread copies the live progress into every caller's mvs::Progress and forwards cancel requests.
 struct Request {
     int32_t ref = 0;
     b200mvs_settings settings;
     b200mvs_maps maps;
-    b200mvs_progress prog;
+    mvs::Progress* progress = nullptr;      // the caller's DMRecon::progress (read by progress printers / UMVE while we run)
+    std::string embedding;
+    bool quiet = true;
     b200mvs_stats stats;
+    std::vector<int32_t> gvs;
     int rc = 0;
     std::string err;
     bool done = false;
@@ -64,12 +74,15 @@ struct DeviceCtx {
     bool cameras_set = false;
     bool leader_active = false;
     std::vector<Request*> pending;
+    uint64_t arrivals = 0;          // bumped by every enqueue: the leader's collection window watches it
+    size_t last_batch = 0;          // size of the previous batch = how many callers to expect
     ~DeviceCtx() { if (ctx) b200mvs_destroy(ctx); }
 };
 
 std::mutex g_mtx;
 std::vector<std::unique_ptr<DeviceCtx>> g_devices;
 std::atomic<unsigned> g_next(0);
+std::mutex g_cout;
 
 std::vector<int> device_list()
 {
@@ -107,32 +120,94 @@ void throw_for(int rc, const std::string& msg)
 
 bool same_settings(const b200mvs_settings& a, const b200mvs_settings& b) { return std::memcmp(&a, &b, sizeof(a)) == 0; }
 
-// Runs one batch on the device context (called by the leader WITHOUT holding D.mtx for the GPU work itself).
-void run_batch(DeviceCtx& D, std::vector<Request*>& batch)
+// Global view selection + colour images of one request (dmrecon.cc:211-241), done by the batch leader.
+// Called WITHOUT D.mtx (D.uploaded is only touched by the leader).
+void prepare_request(DeviceCtx& D, Request& r)
 {
-    while (!batch.empty()) {
-        std::vector<int32_t> refs;
-        std::vector<b200mvs_maps> maps;
-        std::vector<b200mvs_progress> prog;
-        for (Request* r : batch) { refs.push_back(r->ref); maps.push_back(r->maps); prog.push_back(r->prog); }
+    mve::Scene::ViewList const& mve_views(D.scene->get_views());
+    r.progress->status = mvs::RECON_GLOBALVS;
+    int32_t ids[B200MVS_MAX_GLOBAL_VIEWS];
+    const int n = b200mvs_global_view_selection(D.ctx, &r.settings, r.ref, ids, B200MVS_MAX_GLOBAL_VIEWS);
+    if (n < 0) { r.rc = n; r.err = b200mvs_last_error(D.ctx); return; }
+    if (n == 0) { r.rc = B200MVS_ERR_GLOBAL_VS; r.err = "Global View Selection failed"; return; }
+    r.gvs.assign(ids, ids + n);
+    if (!r.quiet) {
+        std::lock_guard<std::mutex> lk(g_cout);
+        std::cout << "Global View Selection:";
+        for (int i = 0; i < n; ++i) std::cout << " " << ids[i];
+        std::cout << std::endl << "Loading color images..." << std::endl;
+    }
+    std::vector<int> need(ids, ids + n);
+    need.push_back(r.ref);
+    for (int id : need) {
+        if (r.progress->cancelled) return;
+        if (D.uploaded[id]) continue;
+        mve::View::Ptr v = mve_views[id];
+        mve::ByteImage::Ptr img = v->get_byte_image(r.embedding);
+        mve::CameraInfo const& cam = v->get_camera();
+        const int rc = b200mvs_upload_view(D.ctx, id, img->get_data_pointer(), img->width(), img->height(), img->channels(),
+            cam.flen, cam.paspect, cam.ppoint, cam.rot, cam.trans);
+        v->cache_cleanup();
+        if (rc != 0) { r.rc = rc; r.err = b200mvs_last_error(D.ctx); return; }
+        D.uploaded[id] = 1;
+    }
+    r.progress->status = mvs::RECON_FEATURES;
+}
+
+// Runs one batch on the device context (called by the leader WITHOUT holding D.mtx).
+void run_batch(DeviceCtx& D, std::vector<Request*> batch)
+{
+    for (Request* r : batch) prepare_request(D, *r);
+    // requests that failed in preparation or were cancelled meanwhile leave the batch with their own result
+    std::vector<Request*> live;
+    for (Request* r : batch) {
+        if (r->rc != 0) continue;
+        if (r->progress->cancelled) { r->rc = B200MVS_ERR_CANCELLED; continue; }
+        live.push_back(r);
+    }
+    while (!live.empty()) {
+        const size_t n = live.size();
+        std::vector<int32_t> refs(n);
+        std::vector<b200mvs_maps> maps(n);
+        std::vector<b200mvs_progress> prog(n);
+        std::memset(prog.data(), 0, sizeof(b200mvs_progress) * n);
+        for (size_t i = 0; i < n; ++i) { refs[i] = live[i]->ref; maps[i] = live[i]->maps; live[i]->progress->status = mvs::RECON_QUEUE; }
+        // relay: live progress out, cancel requests in (Progress is read/written without locks in the reference too,
+        // fancy_progress_printer.cc:84-91, apps/umve/viewinspect/imageoperations.cc:177-184)
+        std::atomic<bool> stop(false);
+        std::thread relay([&]() {
+            while (!stop.load()) {
+                for (size_t i = 0; i < n; ++i) {
+                    live[i]->progress->filled = prog[i].filled;
+                    live[i]->progress->queueSize = prog[i].queue_size;
+                    if (live[i]->progress->cancelled) prog[i].cancelled = 1;
+                }
+                std::this_thread::sleep_for(std::chrono::milliseconds(2));
+            }
+        });
         b200mvs_stats stats;
         int32_t failed = -1;
-        const int rc = b200mvs_reconstruct(D.ctx, &batch[0]->settings, (int)batch.size(), refs.data(), maps.data(), prog.data(),
-                                           &stats, &failed);
+        const int rc = b200mvs_reconstruct(D.ctx, &live[0]->settings, (int)n, refs.data(), maps.data(), prog.data(), &stats, &failed);
+        stop = true;
+        relay.join();
         if (rc == 0 || rc == B200MVS_ERR_CANCELLED) {
-            for (size_t i = 0; i < batch.size(); ++i) {
-                batch[i]->rc = rc; batch[i]->prog = prog[i]; batch[i]->maps = maps[i]; batch[i]->stats = stats;
-                batch[i]->err = rc ? b200mvs_last_error(D.ctx) : "";
+            for (size_t i = 0; i < n; ++i) {
+                // a cancelled view ends as RECON_CANCELLED; the other views of the batch keep their results
+                const bool cancelled = rc == B200MVS_ERR_CANCELLED || prog[i].status == 5;
+                live[i]->rc = cancelled ? B200MVS_ERR_CANCELLED : 0;
+                live[i]->progress->filled = prog[i].filled;
+                live[i]->maps = maps[i]; live[i]->stats = stats;
+                live[i]->err = cancelled ? "reconstruction cancelled" : "";
             }
             return;
         }
-        // one view made the call fail (e.g. "Global View Selection failed"): give it its error, retry the others
+        // one view made the call fail: give it its error, retry the others
         const std::string msg = b200mvs_last_error(D.ctx);
         bool removed = false;
-        for (size_t i = 0; i < batch.size(); ++i) {
-            if (failed >= 0 && batch[i]->ref != failed) continue;
-            batch[i]->rc = rc; batch[i]->err = msg;
-            if (failed >= 0) { batch.erase(batch.begin() + i); removed = true; break; }
+        for (size_t i = 0; i < live.size(); ++i) {
+            if (failed >= 0 && live[i]->ref != failed) continue;
+            live[i]->rc = rc; live[i]->err = msg;
+            if (failed >= 0) { live.erase(live.begin() + i); removed = true; break; }
         }
         if (failed < 0 || !removed) return;      // error not attributable to one view: every request got it
     }
@@ -180,7 +255,7 @@ DMRecon::start()
     DeviceCtx& D = pick_device_ctx();
     std::unique_lock<std::mutex> lock(D.mtx);
 
-    /* (Re)create the device context for this scene. */
+    /* (Re)create the device context for this scene; cameras and features are registered once per context. */
     if (D.ctx == nullptr || D.scene != scene || D.embedding != settings.imageEmbedding) {
         while (D.leader_active) D.cv.wait(lock);
         if (D.ctx) { b200mvs_destroy(D.ctx); D.ctx = nullptr; }
@@ -195,7 +270,7 @@ DMRecon::start()
     b200mvs_ctx* ctx = D.ctx;
 
     /* Views: the same validity test as dmrecon.cc:62-71.  Every valid view gets its camera registered
-       (SingleView::create); colour images are loaded further down, only for the master view and its selected
+       (SingleView::create); colour images are loaded by the batch leader, only for the master views and their selected
        neighbours (loadColorImage, dmrecon.cc:78,238-240), once per view and context. */
     progress.status = RECON_FEATURES;
     if (!D.cameras_set) {
@@ -242,37 +317,8 @@ DMRecon::start()
     s.scale = settings.scale;
     s.use_color_scale = settings.useColorScale ? 1 : 0;
     for (int i = 0; i < 3; ++i) { s.aabb_min[i] = settings.aabbMin[i]; s.aabb_max[i] = settings.aabbMax[i]; }
-
-    /* globalViewSelection (dmrecon.cc:211-241) decides which colour images are needed. */
-    progress.status = RECON_GLOBALVS;
-    {
-        int32_t ids[B200MVS_MAX_GLOBAL_VIEWS];
-        while (D.leader_active) D.cv.wait(lock);
-        int n = b200mvs_global_view_selection(ctx, &s, (int)settings.refViewNr, ids, B200MVS_MAX_GLOBAL_VIEWS);
-        if (n < 0) throw_for(n, b200mvs_last_error(ctx));
-        if (n == 0) throw std::runtime_error("Global View Selection failed");
-        if (!settings.quiet) {
-            std::cout << "Global View Selection:";
-            for (int i = 0; i < n; ++i) std::cout << " " << ids[i];
-            std::cout << std::endl << "Loading color images..." << std::endl;
-        }
-        std::vector<int> need(ids, ids + n);
-        need.push_back((int)settings.refViewNr);
-        for (int id : need) {
-            if (progress.cancelled) break;
-            if (D.uploaded[id]) continue;
-            mve::View::Ptr v = mve_views[id];
-            mve::ByteImage::Ptr img = v->get_byte_image(settings.imageEmbedding);
-            mve::CameraInfo const& cam = v->get_camera();
-            while (D.leader_active) D.cv.wait(lock);      // uploads change the context: not while a batch is running
-            int rc = b200mvs_upload_view(ctx, id, img->get_data_pointer(), img->width(), img->height(), img->channels(),
-                cam.flen, cam.paspect, cam.ppoint, cam.rot, cam.trans);
-            v->cache_cleanup();
-            if (rc != 0) throw_for(rc, b200mvs_last_error(ctx));
-            D.uploaded[id] = 1;
-        }
-    }
-    if (progress.cancelled) { progress.status = RECON_CANCELLED; return; }
+    if (const char* e = std::getenv("B200MVS_FRONTIER_TOPK")) s.frontier_topk = (uint32_t)std::atoi(e);   // engine knobs, include/b200mvs.h
+    if (const char* e = std::getenv("B200MVS_FRONTIER_BAND")) s.frontier_band = (float)std::atof(e);
 
     /* Result images, allocated like SingleView::prepareMasterView (single_view.cc:78-81). */
     mve::FloatImage::Ptr depthImg = mve::FloatImage::create(width, height, 1);
@@ -281,27 +327,42 @@ DMRecon::start()
     Request req;
     req.ref = (int32_t)settings.refViewNr;
     req.settings = s;
+    req.progress = &progress;
+    req.embedding = settings.imageEmbedding;
+    req.quiet = settings.quiet;
     std::memset(&req.maps, 0, sizeof(req.maps));
     req.maps.depth = depthImg->get_data_pointer();
     req.maps.dz = dzImg->get_data_pointer();
     req.maps.conf = confImg->get_data_pointer();
-    std::memset(&req.prog, 0, sizeof(req.prog));
-    req.prog.cancelled = progress.cancelled ? 1 : 0;
     std::memset(&req.stats, 0, sizeof(req.stats));
-    progress.status = RECON_QUEUE;
 
-    /* Submit: whoever finds no leader runs the batches until the queue is empty. */
+    /* Submit.  Whoever finds no leader becomes one and runs batches until the queue is empty. */
     D.pending.push_back(&req);
+    D.arrivals++;
+    D.cv.notify_all();
     if (!D.leader_active) {
         D.leader_active = true;
         while (!D.pending.empty()) {
+            /* Collection window: the other threads of the caller's OpenMP team reach this point within microseconds to
+               milliseconds of each other (they all finished the previous batch together).  Wait until as many requests
+               as the previous batch had are here, or nothing new has arrived for 3 ms, at most 30 ms. */
+            const auto t_open = std::chrono::steady_clock::now();
+            uint64_t seen = D.arrivals;
+            for (;;) {
+                if (D.last_batch > 1 && D.pending.size() >= D.last_batch) break;
+                const bool woke = D.cv.wait_for(lock, std::chrono::milliseconds(3), [&]() { return D.arrivals != seen; });
+                if (!woke) break;
+                seen = D.arrivals;
+                if (std::chrono::steady_clock::now() - t_open > std::chrono::milliseconds(30)) break;
+            }
             std::vector<Request*> batch;
             std::vector<Request*> rest;
-            for (Request* r : D.pending) (batch.empty() || same_settings(r->settings, batch[0]->settings) ? batch : rest).push_back(r);
+            for (Request* r : D.pending)
+                (batch.empty() || (same_settings(r->settings, batch[0]->settings) && r->embedding == batch[0]->embedding) ? batch : rest).push_back(r);
             D.pending.swap(rest);
-            std::vector<Request*> running(batch);
+            D.last_batch = batch.size();
             lock.unlock();
-            run_batch(D, running);
+            run_batch(D, batch);
             lock.lock();
             for (Request* r : batch) r->done = true;
             D.cv.notify_all();
@@ -314,17 +375,34 @@ DMRecon::start()
 
     const b200mvs_stats& stats = req.stats;
     const int rc0 = req.rc;
-    progress.filled = req.prog.filled;
     progress.queueSize = 0;
     if (rc0 == B200MVS_ERR_CANCELLED || progress.cancelled) { progress.status = RECON_CANCELLED; return; }
     if (rc0 != 0) throw_for(rc0, req.err);
     if (!settings.quiet)
-        std::cout << "Reconstructed view " << settings.refViewNr << " (batched with the views in flight: " << stats.n_seeds_processed
+        std::cout << "Reconstructed view " << settings.refViewNr << " (batch of all views in flight: " << stats.n_seeds_processed
                   << " features processed, " << stats.n_seeds_success << " succeeded optimization, " << stats.n_rounds
                   << " frontier rounds)." << std::endl;
 
     progress.status = RECON_SAVING;
     mve::View::Ptr view = mve_views[settings.refViewNr];
+    mve::ByteImage::Ptr scaled;
+    if (settings.scale != 0 || settings.writePlyFile) {
+        // level `scale` of the reference view as the device built it (bit-exact with the reference's pyramid)
+        scaled = mve::ByteImage::create(width, height, 3);
+        int w = 0, h = 0;
+        int rc = b200mvs_get_level(ctx, (int)settings.refViewNr, settings.scale, &w, &h, scaled->get_data_pointer());
+        if (rc != 0) throw_for(rc, b200mvs_last_error(ctx));
+    }
+    if (settings.writePlyFile) {
+        // SingleView::saveReconAsPly (single_view.cc:123-138) through the same libmve writers
+        if (settings.plyPath.empty()) throw std::invalid_argument("Empty path");
+        std::string fname = "mvs-" + util::string::get_filled(settings.refViewNr, 4) + "-L" + util::string::get((float)settings.scale);
+        if (!settings.quiet)
+            std::cout << "Saving ply file as " << settings.plyPath << "/" << fname << ".ply" << std::endl;
+        if (!util::fs::dir_exists(settings.plyPath.c_str())) util::fs::mkdir(settings.plyPath.c_str());
+        mve::geom::save_ply_view(util::fs::join_path(settings.plyPath, fname + ".ply"), view->get_camera(), depthImg, confImg, scaled);
+        mve::geom::save_xf_file(util::fs::join_path(settings.plyPath, fname + ".xf"), view->get_camera());
+    }
     std::string name("depth-L");
     name += util::string::get(settings.scale);
     view->set_image(depthImg, name);
@@ -339,10 +417,6 @@ DMRecon::start()
         view->set_image(confImg, name);
     }
     if (settings.scale != 0) {
-        mve::ByteImage::Ptr scaled = mve::ByteImage::create(width, height, 3);
-        int w = 0, h = 0;
-        int rc = b200mvs_get_level(ctx, (int)settings.refViewNr, settings.scale, &w, &h, scaled->get_data_pointer());
-        if (rc != 0) throw_for(rc, b200mvs_last_error(ctx));
         name = "undist-L";
         name += util::string::get(settings.scale);
         view->set_image(scaled, name);

@@ -44,3 +44,62 @@ def test_cli_writes_reference_layout(name, views):
         # resume semantics live in the unchanged driver: a second run without --force skips finished views
         out2 = subprocess.run([c for c in cmd if c != "--force"], capture_output=True, text=True, timeout=600)
         assert out2.returncode == 0
+
+
+REF_CLI = os.path.join(ROOT, "oracle", "_ref", "dmrecon")
+
+
+def _read_ply_vertices(path):
+    """Binary little-endian PLY of mve::geom::save_ply_view: returns (n_vertices, n_faces, vertex block bytes)."""
+    raw = open(path, "rb").read()
+    end = raw.index(b"end_header\n") + len(b"end_header\n")
+    head = raw[:end].decode("ascii", "replace")
+    nv = int([l for l in head.splitlines() if l.startswith("element vertex")][0].split()[-1])
+    nf = int(([l for l in head.splitlines() if l.startswith("element face")] or ["element face 0"])[0].split()[-1])
+    return nv, nf, head, raw[end:]
+
+
+@pytest.mark.skipif(not (os.path.exists(CLI) and os.path.exists(REF_CLI)), reason="drop-in or reference CLI not built")
+def test_cli_writes_ply_like_the_reference():
+    """-p / --writeply (settings.writePlyFile, plyPath; dmrecon.cc:109-117, single_view.cc:123-138): the drop-in writes
+    mvs-<id>-L<s>.ply / .xf through the same libmve writers; vertex and face counts follow the depth map, so they agree with
+    the reference's file up to the pixels on which the maps differ, the .xf files are identical."""
+    from mve_b200 import synth
+    s = golden_scene("T0")
+    with tempfile.TemporaryDirectory() as t1, tempfile.TemporaryDirectory() as t2:
+        outs = []
+        for exe, tmp in ((CLI, t1), (REF_CLI, t2)):
+            synth.write_mve_scene(s, tmp)
+            cmd = [exe, "-s%d" % s.scale, "--progress=silent", "--force", "-p", "--plydest=plyout", "-l0,3", tmp]
+            out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, OMP_NUM_THREADS="2"))
+            assert out.returncode == 0, out.stdout + out.stderr
+            outs.append(out.stdout)
+        for v in (0, 3):
+            name = "mvs-%04d-L%d" % (v, s.scale)
+            a = os.path.join(t1, "plyout", name + ".ply")
+            b = os.path.join(t2, "plyout", name + ".ply")
+            assert os.path.exists(a) and os.path.exists(b)
+            assert open(os.path.join(t1, "plyout", name + ".xf")).read() == open(os.path.join(t2, "plyout", name + ".xf")).read()
+            nva, nfa, ha, _ = _read_ply_vertices(a)
+            nvb, nfb, hb, _ = _read_ply_vertices(b)
+            assert [l for l in ha.splitlines() if l.startswith("property")] == [l for l in hb.splitlines() if l.startswith("property")]
+            assert abs(nva - nvb) <= 0.01 * nvb + 5 and abs(nfa - nfb) <= 0.03 * nfb + 20, (nva, nvb, nfa, nfb)
+
+
+@pytest.mark.skipif(not os.path.exists(CLI), reason="shim/_build/dmrecon_b200 not built")
+def test_cli_batches_the_views_in_flight():
+    """The OpenMP threads of the unmodified driver (apps/dmrecon/dmrecon.cc:285) are combined into ONE b200mvs_reconstruct per
+    GPU: with 6 views on 6 threads every 'Reconstructed view' line reports the features of the whole batch."""
+    import re
+    from mve_b200 import synth
+    s = golden_scene("T0")
+    with tempfile.TemporaryDirectory() as tmp:
+        synth.write_mve_scene(s, tmp)
+        cmd = [CLI, "-s%d" % s.scale, "--progress=simple", "--force", tmp]
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, OMP_NUM_THREADS="6"))
+        assert out.returncode == 0, out.stdout + out.stderr
+        feats = [int(m) for m in re.findall(r"batch of all views in flight: (\d+) features processed", out.stdout)]
+        assert len(feats) == s.n_views
+        single = subprocess.run([CLI, "-s%d" % s.scale, "--progress=simple", "--force", "-l0", tmp], capture_output=True, text=True, timeout=600)
+        one = int(re.findall(r"batch of all views in flight: (\d+) features processed", single.stdout)[0])
+        assert max(feats) >= 3 * one, (feats, one)       # at least half of the team ended up in one batch

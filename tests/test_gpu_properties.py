@@ -228,6 +228,35 @@ def test_cancel_while_running():
     assert 200 < prog[0].filled < stats_full.n_filled
 
 
+def test_cancel_one_view_of_a_batch():
+    """Cancelling ONE view of a running batch drops only that view's queue (status RECON_CANCELLED, no maps); the other
+    view finishes with exactly the maps it gets alone."""
+    import threading
+    import time
+    from mve_b200 import dmrecon
+    s = golden_scene("T1")
+    g = dmrecon.Scene.from_synth(s)
+    st = dmrecon.Settings(scale=s.scale, frontier_topk=4)
+    alone, _ = g.reconstruct(st, [2])
+    prog = (dmrecon.Progress * 2)()
+
+    def canceller():
+        t0 = time.time()
+        while time.time() - t0 < 20.0:
+            if prog[1].filled > 200:
+                prog[1].cancelled = 1
+                return
+            time.sleep(0.0005)
+    th = threading.Thread(target=canceller)
+    th.start()
+    maps, stats = g.reconstruct(st, [2, 4], progress=prog)
+    th.join()
+    assert prog[1].status == 5 and prog[0].status == 0
+    assert 200 < prog[1].filled
+    for k in ("depth", "conf", "dz", "view_ids"):
+        assert (maps[0][k] == alone[0][k]).all()
+
+
 def test_image_channel_variants():
     """Grey and RGBA inputs are expanded / stripped like image_pyramid.cc:65-73."""
     from mve_b200 import dmrecon
