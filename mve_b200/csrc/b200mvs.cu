@@ -2,12 +2,14 @@
 // frontier (region growing) orchestration and all CUDA kernels.  sm_100a only; no CPU fallback.
 #include "../../include/b200mvs.h"
 #include "patch_opt.cuh"
+#include "patch_thread.cuh"
 
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <map>
 #include <chrono>
 #include <ctime>
@@ -134,6 +136,8 @@ struct b200mvs_ctx {
     DevBuf<int> job_cancel;
     int frontier_grid = 0;             // CTAs of the cooperative launch (= what fits on the chip)
     int optimize_grid = 0;             // resident CTAs of k_optimize
+    long long thread_min = -1;         // reconstruct: rounds with at least this many patches run one thread per patch (-1: default)
+    int optimize_mode = 0;             // b200mvs_optimize_patches: 0 by batch size, 1 eight lanes per patch, 2 one thread per patch
     unsigned long long* h_counters = nullptr;   // pinned
     unsigned long long* h_mirror = nullptr;     // pinned + mapped: HostMirror
     std::vector<cudaEvent_t> ev_pool;
@@ -460,7 +464,8 @@ __global__ void k_export_rgb(const uchar4* __restrict__ src, int w, int h, int p
 constexpr int OPT_WARPS = OPT_TPB / 32;
 // dynamic shared memory of the kernels that optimise patches: the lane-replicated sRGB table
 constexpr size_t OPT_SMEM_BYTES = sizeof(float) * (256 * LUT_REP);
-using PatchT = Patch;
+using PatchT = Patch;        // 8 lanes per patch (latency: small rounds)
+using PatchT1 = b200mvs::PatchT;   // one thread per patch (throughput: large rounds)
 
 __device__ __forceinline__ Entry load_entry(const Entry* p)       // lists are rewritten by other SMs every round: bypass L1
 {
@@ -470,14 +475,6 @@ __device__ __forceinline__ Entry load_entry(const Entry* p)       // lists are r
     e.xy = a.x; e.jobdir = a.y; e.conf = __int_as_float(a.z); e.depth = __int_as_float(a.w);
     e.dzI = __int_as_float(b.x); e.dzJ = __int_as_float(b.y); e.slots = (unsigned)b.z; e.pad = b.w;
     return e;
-}
-
-// Fills the shared memory of a patch-optimisation kernel and binds the thread to its 8-lane group.
-__device__ __forceinline__ void opt_setup(PatchT& p, float* smem, const float* g_lut, const DevSettings* st, const ViewParams* views)
-{
-    for (int i = threadIdx.x; i < 256 * LUT_REP; i += blockDim.x) smem[i] = g_lut[i / LUT_REP];
-    __syncthreads();
-    bind_thread(p, st, views, smem, (int)threadIdx.x);
 }
 
 // The PatchOptimizations of list[0..n): every 8-lane group takes entries through the ticket counter until none is left; a
@@ -518,16 +515,71 @@ __device__ __forceinline__ void optimise_entries(PatchT& p, const Entry* list, P
     }
 }
 
-// A batch of independent PatchOptimizations (b200mvs_optimize_patches).
+// The same for LARGE lists: one thread per entry (patch_thread.cuh).  Lanes that need an entry take consecutive tickets with
+// one atomic per converged subset of the warp; like the groups above, a lane that finishes fetches its next entry at once
+// and meets the other lanes of its warp again at the pass() call site.
+__device__ __forceinline__ void optimise_entries_t(PatchT1& p, const Entry* list, PatchOut* res, unsigned long long n,
+                                                   unsigned long long* ticket, const JobParams* jobs, unsigned long long* counters)
+{
+    const int lane = threadIdx.x & 31;
+    bool have = false;
+    unsigned long long idx = 0ull;
+    unsigned opts = 0u;
+    for (;;) {
+        if (!have) {
+            const unsigned act = __activemask();
+            const int leader = __ffs(act) - 1;
+            unsigned long long base = 0ull;
+            if (lane == leader) base = atomicAdd(ticket, (unsigned long long)__popc(act));
+            base = __shfl_sync(act, base, leader);
+            const unsigned long long w = base + (unsigned long long)__popc(act & ((1u << lane) - 1u));
+            if (w >= n) break;
+            idx = w;
+            const Entry e = load_entry(&list[w]);
+            PatchIn pi;
+            pi.x = e.xy & 0xFFFF; pi.y = (e.xy >> 16) & 0xFFFF;
+            pi.depth = e.depth; pi.dzI = e.dzI; pi.dzJ = e.dzJ; pi.slots = e.slots;
+            p.begin(&jobs[e.jobdir & 0xFFFFFF], pi);
+            have = true;
+            ++opts;
+        }
+        if (p.step()) {
+            PatchOut po;
+            p.finish(po);
+            res[idx] = po;
+            have = false;
+        }
+    }
+    if (opts) {
+        atomicAdd(&counters[C_SETS], (unsigned long long)p.n_sets);
+        atomicAdd(&counters[C_OPTS], (unsigned long long)opts);
+        p.n_sets = 0u;
+    }
+}
+
+#ifndef OPT_THREAD_MIN
+#define OPT_THREAD_MIN 16384   // lists at least this long are optimised one thread per patch, shorter ones 8 lanes per patch
+#endif
+
+// A batch of independent PatchOptimizations (b200mvs_optimize_patches).  mode: 0 = by list length, 1 = 8 lanes per patch,
+// 2 = one thread per patch.
 __global__ void __launch_bounds__(OPT_TPB, OPT_MIN_BLOCKS)
-k_optimize(const Entry* __restrict__ in, PatchOut* __restrict__ out, int n,
+k_optimize(const Entry* __restrict__ in, PatchOut* __restrict__ out, int n, int mode,
            const DevSettings* __restrict__ st, const JobParams* __restrict__ jobs, const ViewParams* __restrict__ views,
            const float* __restrict__ g_lut, unsigned long long* counters)
 {
     extern __shared__ float smem[];
-    PatchT p;
-    opt_setup(p, smem, g_lut, st, views);
-    optimise_entries(p, in, out, (unsigned long long)n, &counters[C_TICKET], jobs, counters);
+    for (int i = threadIdx.x; i < 256 * LUT_REP; i += blockDim.x) smem[i] = g_lut[i / LUT_REP];
+    __syncthreads();
+    if (mode == 2 || (mode == 0 && n >= OPT_THREAD_MIN)) {
+        PatchT1 p;
+        bind_thread(p, st, views, smem, (int)threadIdx.x);
+        optimise_entries_t(p, in, out, (unsigned long long)n, &counters[C_TICKET], jobs, counters);
+    } else {
+        PatchT p;
+        bind_thread(p, st, views, smem, (int)threadIdx.x);
+        optimise_entries(p, in, out, (unsigned long long)n, &counters[C_TICKET], jobs, counters);
+    }
 }
 
 __device__ __forceinline__ unsigned long long entry_key(const Entry& e)
@@ -561,6 +613,7 @@ struct FrontierParams {
     volatile unsigned long long* host_filled;   // [n_jobs], mapped
     volatile int* host_cancel_job;              // [n_jobs], mapped
     int* job_cancel;                            // [n_jobs], device copy refreshed every round
+    long long thread_min;                       // rounds with at least this many patches run one thread per patch
     int band_bins;                              // frontier_band in fine bins (0 = off)
     int topk;                                   // frontier_topk (0 = off)
 };
@@ -680,8 +733,8 @@ __global__ void __launch_bounds__(OPT_TPB, OPT_MIN_BLOCKS)
 k_frontier(const FrontierParams P)
 {
     extern __shared__ float smem[];
-    PatchT patch;
-    opt_setup(patch, smem, P.lut, P.st, P.views);
+    for (int i = threadIdx.x; i < 256 * LUT_REP; i += blockDim.x) smem[i] = P.lut[i / LUT_REP];
+    __syncthreads();
     const int lane = threadIdx.x & 31;
     const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, gthreads = (size_t)gridDim.x * blockDim.x;
     FrontierCtl* const ctl = P.ctl;
@@ -768,7 +821,15 @@ k_frontier(const FrontierParams P)
         if (lead) ctl->nlist[p] = 0ull;                           // consumed; the round after the next pushes into it
         }
         // the PatchOptimizations of the round
-        optimise_entries(patch, P.run, P.res, n_run, &ctl->ticket, P.jobs, cnt);
+        if (n_run >= (unsigned long long)P.thread_min) {
+            PatchT1 pt;
+            bind_thread(pt, P.st, P.views, smem, (int)threadIdx.x);
+            optimise_entries_t(pt, P.run, P.res, n_run, &ctl->ticket, P.jobs, cnt);
+        } else {
+            PatchT pg;
+            bind_thread(pg, P.st, P.views, smem, (int)threadIdx.x);
+            optimise_entries(pg, P.run, P.res, n_run, &ctl->ticket, P.jobs, cnt);
+        }
         if (seed_round) {
             PHASE_END(PH_SEED);
             for (size_t i = gtid; i < (size_t)P.n_seeds; i += gthreads) {
@@ -1259,6 +1320,15 @@ int b200mvs_global_view_selection(b200mvs_ctx* ctx, const b200mvs_settings* s, i
     return (int)sel.size();
 }
 
+int b200mvs_set_patch_mode(b200mvs_ctx* ctx, int mode, int64_t thread_min)
+{
+    if (!ctx || mode < 0 || mode > 2) return B200MVS_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mtx);
+    ctx->optimize_mode = mode;
+    ctx->thread_min = thread_min;
+    return 0;
+}
+
 int b200mvs_plan_views(b200mvs_ctx* ctx, const b200mvs_settings* s, int n_refs, const int32_t* refs)
 {
     if (!ctx) return B200MVS_ERR_INVALID_ARG;
@@ -1344,7 +1414,7 @@ int b200mvs_optimize_patches(b200mvs_ctx* ctx, const b200mvs_settings* s, int re
         if (rc2) return rc2;
         const int groups_per_block = OPT_TPB / GROUP;
         const int grid = std::max(1, std::min((n + groups_per_block - 1) / groups_per_block, ctx->optimize_grid));
-        k_optimize<<<grid, OPT_TPB, OPT_SMEM_BYTES, st>>>(ctx->run_in.p, ctx->run_out.p, n, ctx->d_settings.p,
+        k_optimize<<<grid, OPT_TPB, OPT_SMEM_BYTES, st>>>(ctx->run_in.p, ctx->run_out.p, n, ctx->optimize_mode, ctx->d_settings.p,
                                                           ctx->d_jobs.p, ctx->d_views, ctx->d_lut, ctx->counters.p);
     }
     CK(cudaGetLastError());
@@ -1528,6 +1598,8 @@ int b200mvs_reconstruct(b200mvs_ctx* ctx, const b200mvs_settings* s, int n_refs,
     P.st = ctx->d_settings.p; P.jobs = ctx->d_jobs.p; P.views = ctx->d_views; P.lut = ctx->d_lut;
     P.counters = ctx->counters.p; P.ctl = ctx->ctl.p; P.hist = ctx->hist.p; P.thr_bin = ctx->thr_bin.p;
     P.host = mirror; P.host_filled = m_filled; P.host_cancel_job = m_cancel_job; P.job_cancel = ctx->job_cancel.p;
+    P.thread_min = ctx->thread_min >= 0 ? ctx->thread_min : OPT_THREAD_MIN;
+    if (const char* e = std::getenv("B200MVS_THREAD_MIN")) P.thread_min = std::atoll(e);      // tuning knob (tools/kbench.py)
     P.band_bins = s->frontier_band > 0.f ? std::max(1, (int)(s->frontier_band * (float)HIST_FINE)) : 0;
     P.topk = (int)std::min<uint32_t>(s->frontier_topk, 1u << 30);
 

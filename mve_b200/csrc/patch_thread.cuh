@@ -1,0 +1,678 @@
+// Device-side patch optimisation, THROUGHPUT variant: one THREAD per patch (32 patches per warp).
+//
+// Same function as Patch in patch_opt.cuh - one mvs::PatchOptimization of the reference
+// (libs/dmrecon/patch_optimization.cc:21-364 with PatchSampler patch_sampler.cc:19-393, LocalViewSelection
+// local_view_selection.cc:19-160 and mvs_tools.cc:98-199) - organised for large frontier rounds, where there are far more
+// queue entries than lanes on the chip:
+//   * a lane walks the 25 samples of its own patch in a rolled loop, so no lane idles on a 25-of-32 mapping, nothing is
+//     reduced across lanes (no shuffles at all) and everything that is uniform per patch - view constants, level choice,
+//     colour scales, the state machine - is paid once per 32 patches instead of once per patch;
+//   * nothing per-sample survives an iteration of the sample loop: the sums the reference forms in separate passes over
+//     stored samples are accumulated in ONE sweep, in forms that do not need the means or the updated colour scale first:
+//       NCC (patch_sampler.cc:143-162)      sum(n-p), sum((n-p)^2), sum(e (n-p)) around the pivot p = meanX * masterMeanCol
+//                                           (the neighbour colours scatter around it, so the variance is formed without
+//                                           cancellation)
+//       colour scale (patch_optimization.cc:88-110)   sum(m n), sum(n n)  ->  ab = sum(m n) - cs * sum(n n)
+//       Gauss-Newton, depth only, when the colour scale changes at this state (:283-288)
+//                                           sum(d m), sum(d n), sum(d d) per channel -> numerator / denominator with the NEW scale
+//       otherwise the products of :283-288 / :324-343 directly with the current scale;
+//     only a view replacement (colour scale AND normal step at one state, rare) sweeps a view twice;
+//   * geometry per sample is evaluated in the neighbour's camera frame directly: with u = R^T K^-1 (x, y, 1) the patch point
+//     is C + t u / |u| and its image W (C + t u/|u|) + T = (W C + T) + (t / |u|) (W u); W C + T and W u0, W ua, W ub (u is
+//     affine in the pixel offsets) are formed once per view and sweep - 12 FMAs per sample for BOTH projections of
+//     patch_sampler.cc:94-133 instead of two full point transforms.  Same values up to rounding order (<= 2 ulp on pixel
+//     coordinates; measured against the oracle in tests/test_gpu_parity.py and on the CPU in
+//     tests/test_device_code_emulated.py).
+// The state machine (stages, iteration counting, view replacement) is the one of Patch::step() statement for statement.
+#pragma once
+#include "patch_opt.cuh"
+
+namespace b200mvs {
+
+struct PatchT {
+    // ---- constants of the thread ----
+    const DevSettings* st;
+    const ViewParams* views;
+    const float* lutw;         // replicated srgb2lin table + lane: value v of this lane at lutw[v * LUT_REP]
+    // ---- constants of the patch ----
+    const JobParams* job;
+    const ViewParams* rv;
+    int x0, y0;
+    float u0x, u0y, u0z;       // R^T K^-1 (x + .5, y + .5, 1): un-normalised ray of the centre pixel
+    float uax, uay, uaz;       // R^T K^-1 (1, 0, 0): change of the ray per pixel in x
+    float ubx, uby, ubz;       // R^T K^-1 (0, 1, 0): ... in y
+    float c0x, c0y, c0z;       // camera centre of the reference view
+    float mx0, mx1, mx2;       // meanX per channel (patch_sampler.cc:333-339)
+    float crx, cry, crz;       // masterViewDirs[12]
+    float cpx, cpy, cpz;       // patchPoints[12]
+    float mfp, inv_mfp;        // footPrintScaled(patchPoints[12]) and its reciprocal
+    float mm, inv_mm, sqrDevX; // masterMeanCol, its reciprocal, sqrDevX
+    float depth, dzI, dzJ;
+    bool ref_ok;               // sampler->success[refViewNr]
+    int nsel;
+    unsigned avail;            // LocalViewSelection::available over global slots
+    int iter;
+    bool opti, converged, lvs_ok;
+    unsigned n_sets;
+    int stage;
+    bool viewRemoved, was_normal, normal;
+    // ---- per selected view (index = position in the ascending selected set) ----
+    int sel[MAX_LOCAL];        // global slot, 0xFF = none
+    float cs[MAX_LOCAL][3];    // colorScale
+    float ncc[MAX_LOCAL];      // NCC at the state of the last pass
+    float oldn[MAX_LOCAL];     // oldNCC
+    float cand[MAX_GLOBAL];    // NCC of candidate global slots (local view selection; rare path, may live in local memory)
+    // ---- results of the last pass ----
+    unsigned p_col_ok, p_der_ok;
+    float p_num, p_den;
+    float nX0, nX1, nX2;
+    bool n_singular;
+    bool p_has_normal, p_has_ncc;
+
+    enum Stage { LVS_CTOR, CTOR, FIRST, PRE, POST, LVS_REPL, REPL, DONE };
+
+    // ---- register arrays with a dynamic index ----
+    template <typename T> static __device__ __forceinline__ T get4(const T (&a)[MAX_LOCAL], int k)
+    {
+        return k == 0 ? a[0] : (k == 1 ? a[1] : (k == 2 ? a[2] : a[3]));
+    }
+    template <typename T> static __device__ __forceinline__ void set4(T (&a)[MAX_LOCAL], int k, T v)
+    {
+#pragma unroll
+        for (int i = 0; i < MAX_LOCAL; ++i) if (i == k) a[i] = v;
+    }
+
+    // un-normalised ray of the sample with pixel offsets (di, dj), its reciprocal length and the sample's depth parameter
+    __device__ __forceinline__ void sample_ray(float di, float dj, float& ux, float& uy, float& uz, float& inv) const
+    {
+        ux = u0x + di * uax + dj * ubx;
+        uy = u0y + di * uay + dj * uby;
+        uz = u0z + di * uaz + dj * ubz;
+        inv = rsqrt_fast(ux * ux + uy * uy + uz * uz);
+    }
+
+    // patch_sampler.cc:274-295 (+ the centre point / master footprint used by every sample set)
+    __device__ __forceinline__ void compute_points()
+    {
+        bool bad = false;
+#pragma unroll 5
+        for (int k = 0; k < NS; ++k) {
+            const float t = depth + (float)(k % 5 - 2) * dzI + (float)(k / 5 - 2) * dzJ;
+            bad |= t <= 0.f;
+        }
+        if (bad) ref_ok = false;
+        cpx = c0x + depth * crx;
+        cpy = c0y + depth * cry;
+        cpz = c0z + depth * crz;
+        const float z = __ldg(&rv->w2c[8]) * cpx + __ldg(&rv->w2c[9]) * cpy + __ldg(&rv->w2c[10]) * cpz + __ldg(&rv->w2c[11]);
+        mfp = z * job->ki0;     // single_view.h:160-164
+        inv_mfp = rcp_fast(mfp);
+    }
+
+    // PatchSampler ctor (patch_sampler.cc:19-62) + computeMasterSamples (:298-345)
+    __device__ __forceinline__ void init_sampler(int x, int y)
+    {
+        ref_ok = false; mm = 0.f; inv_mm = 0.f; sqrDevX = 0.f;
+        mx0 = mx1 = mx2 = 0.f;
+        crx = cry = crz = cpx = cpy = cpz = mfp = inv_mfp = 0.f;
+        if (x - 2 < 0 || y - 2 < 0 || x + 2 > job->W - 1 || y + 2 > job->H - 1) return;
+        {
+            // viewRayScaled (single_view.cc:99-106, depthmap.cc:149-156): K^-1 has the sparsity of camera.cc:180-200
+            const float r0 = __ldg(&rv->rot[0]), r1 = __ldg(&rv->rot[1]), r2 = __ldg(&rv->rot[2]), r3 = __ldg(&rv->rot[3]), r4 = __ldg(&rv->rot[4]);
+            const float r5 = __ldg(&rv->rot[5]), r6 = __ldg(&rv->rot[6]), r7 = __ldg(&rv->rot[7]), r8 = __ldg(&rv->rot[8]);
+            const float vx = job->ki0 * ((float)x + 0.5f) + job->ki2, vy = job->ki4 * ((float)y + 0.5f) + job->ki5;
+            u0x = r0 * vx + r3 * vy + r6; u0y = r1 * vx + r4 * vy + r7; u0z = r2 * vx + r5 * vy + r8;
+            uax = r0 * job->ki0; uay = r1 * job->ki0; uaz = r2 * job->ki0;
+            ubx = r3 * job->ki4; uby = r4 * job->ki4; ubz = r5 * job->ki4;
+            c0x = __ldg(&rv->campos[0]); c0y = __ldg(&rv->campos[1]); c0z = __ldg(&rv->campos[2]);
+            const float inv = rsqrt_fast(u0x * u0x + u0y * u0y + u0z * u0z);
+            crx = u0x * inv; cry = u0y * inv; crz = u0z * inv;
+        }
+        ref_ok = true;
+        // master colours: mean, then the per-channel means and deviations of the normalised colours
+        const uchar4* row = job->ref_img + (size_t)(y - 2) * job->ref_pitch + (x - 2);
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+        for (int j = 0; j < 5; ++j) {
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+                const uchar4 t = row[i];
+                s0 += lutw[t.x * LUT_REP]; s1 += lutw[t.y * LUT_REP]; s2 += lutw[t.z * LUT_REP];
+            }
+            row += job->ref_pitch;
+        }
+        mm = (s0 + s1 + s2) / (3.f * NS);
+        if (mm < 0.01f || mm > 0.99f) { ref_ok = false; return; }
+        inv_mm = 1.f / mm;
+        mx0 = (s0 * inv_mm) / (float)NS; mx1 = (s1 * inv_mm) / (float)NS; mx2 = (s2 * inv_mm) / (float)NS;
+        row = job->ref_img + (size_t)(y - 2) * job->ref_pitch + (x - 2);
+        float dev = 0.f;
+#pragma unroll 1
+        for (int j = 0; j < 5; ++j) {
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+                const uchar4 t = row[i];
+                const float e0 = lutw[t.x * LUT_REP] * inv_mm - mx0, e1 = lutw[t.y * LUT_REP] * inv_mm - mx1, e2 = lutw[t.z * LUT_REP] * inv_mm - mx2;
+                dev += e0 * e0 + e1 * e1 + e2 * e2;
+            }
+            row += job->ref_pitch;
+        }
+        sqrDevX = dev;
+        compute_points();
+    }
+
+    // PatchSampler::update (patch_sampler.cc:259-271)
+    __device__ __forceinline__ void update()
+    {
+        ref_ok = true;
+        compute_points();
+    }
+
+    // One pass at the current state (same contract as Patch::pass).
+    __device__ __forceinline__ void pass(bool candidates, bool cs_pending, bool want_ncc, bool want_normal)
+    {
+        float num = 0.f, den = 0.f;
+        double D0 = 0.0, D1 = 0.0, D2 = 0.0, D3 = 0.0, D4 = 0.0, D5 = 0.0, E0 = 0.0, E1 = 0.0, E2 = 0.0;
+        bool cs_active = cs_pending && st->use_color_scale;
+        if (!candidates) { p_col_ok = p_der_ok = 0u; }
+        const int count = candidates ? job->n_global : nsel;
+        const float pv0 = mx0 * mm, pv1 = mx1 * mm, pv2 = mx2 * mm;      // pivots of the NCC sums
+#pragma unroll 1
+        for (int k = 0; k < count; ++k) {
+            int slot = k;
+            if (candidates) { if (!((avail >> k) & 1u)) continue; }
+            else slot = get4(sel, k);
+            const ViewParams* V = &views[job->gview[slot]];
+            ++n_sets;
+            float c0 = 1.f, c1 = 1.f, c2 = 1.f;
+            if (!candidates) {
+                c0 = k == 0 ? cs[0][0] : (k == 1 ? cs[1][0] : (k == 2 ? cs[2][0] : cs[3][0]));
+                c1 = k == 0 ? cs[0][1] : (k == 1 ? cs[1][1] : (k == 2 ? cs[2][1] : cs[3][1]));
+                c2 = k == 0 ? cs[0][2] : (k == 1 ? cs[1][2] : (k == 2 ? cs[2][2] : cs[3][2]));
+            }
+            // ---- view set-up: transform, level choice (patch_sampler.cc:76-91), derivative step (:94-100) ----
+            unsigned r = 0u;
+            float A0x = 0.f, A0y = 0.f, A0z = 0.f, W0x = 0.f, W0y = 0.f, W0z = 0.f, Wax = 0.f, Way = 0.f, Waz = 0.f, Wbx = 0.f, Wby = 0.f, Wbz = 0.f;
+            float Lax = 0.f, Lay = 0.f, Lcx = 0.f, Lcy = 0.f, wm1 = 0.f, hm1 = 0.f, dd = 0.f, step = 0.f;
+            int Lpitch = 0;
+            const uint4* Lquad = nullptr;
+            bool dok = false;
+            {
+                const float4 wa = __ldg(reinterpret_cast<const float4*>(&V->w2c[0]));
+                const float4 wb = __ldg(reinterpret_cast<const float4*>(&V->w2c[4]));
+                const float4 wc = __ldg(reinterpret_cast<const float4*>(&V->w2c[8]));
+                A0x = wa.x * c0x + wa.y * c0y + wa.z * c0z + wa.w;
+                A0y = wb.x * c0x + wb.y * c0y + wb.z * c0z + wb.w;
+                A0z = wc.x * c0x + wc.y * c0y + wc.z * c0z + wc.w;
+                W0x = wa.x * u0x + wa.y * u0y + wa.z * u0z; W0y = wb.x * u0x + wb.y * u0y + wb.z * u0z; W0z = wc.x * u0x + wc.y * u0y + wc.z * u0z;
+                Wax = wa.x * uax + wa.y * uay + wa.z * uaz; Way = wb.x * uax + wb.y * uay + wb.z * uaz; Waz = wc.x * uax + wc.y * uay + wc.z * uaz;
+                Wbx = wa.x * ubx + wa.y * uby + wa.z * ubz; Wby = wb.x * ubx + wb.y * uby + wb.z * ubz; Wbz = wc.x * ubx + wc.y * uby + wc.z * ubz;
+                const float nz = wc.x * cpx + wc.y * cpy + wc.z * cpz + wc.w;
+                const float nfp = nz * __ldg(&V->inv_ax0);
+                // mfp <= 0 makes the reference throw std::out_of_range (patch_sampler.cc:78-82); it cannot happen for
+                // depth > 0 because the centre ray has positive camera z.  Treated as a failed view here.
+                if (mfp > 0.f && !(nfp <= 0.f)) {
+                    float ratio = nfp * inv_mfp;
+                    int l = 0;
+                    while (ratio < 0.5f) { ++l; ratio *= 2.f; }
+                    const int nl = __ldg(&V->nlevels);
+                    if (l > nl - 1) l = nl - 1;                     // clampLevel, minLevel = 0 (single_view.h:113-123)
+                    const float4 kk = __ldg(reinterpret_cast<const float4*>(&V->lv[l].ax));
+                    const int4 g = __ldg(reinterpret_cast<const int4*>(&V->lv[l].w));
+                    Lax = kk.x; Lay = kk.y; Lcx = kk.z; Lcy = kk.w; wm1 = (float)(g.x - 1); hm1 = (float)(g.y - 1); Lpitch = g.z;
+                    Lquad = reinterpret_cast<const uint4*>(__ldg(reinterpret_cast<const unsigned long long*>(&V->lv[l].quad)));
+                    // projections of patchPoints[12] and patchPoints[12] + masterViewDirs[12]
+                    const float inv0 = rsqrt_fast(u0x * u0x + u0y * u0y + u0z * u0z);
+                    const float sa = depth * inv0, sb = (depth + 1.f) * inv0;
+                    const float hz1 = A0z + sa * W0z, hz2 = A0z + sb * W0z;
+                    const float i1 = rcp_fast(hz1), i2 = rcp_fast(hz2);
+                    const float ddx = (Lax * (A0x + sb * W0x) + Lcx * hz2) * i2 - (Lax * (A0x + sa * W0x) + Lcx * hz1) * i1;
+                    const float ddy = (Lay * (A0y + sb * W0y) + Lcy * hz2) * i2 - (Lay * (A0y + sa * W0y) + Lcy * hz1) * i1;
+                    const float dd2 = ddx * ddx + ddy * ddy;
+                    dd = dd2 * rsqrt_fast(dd2);            // |.|; NaN for dd2 == 0, which fails `d > 0` like the reference's 0
+                    dok = dd > 0.f;
+                    step = rcp_fast(dd);
+                    r = dok ? 3u : 1u;
+                }
+            }
+            const bool need_ncc = candidates || want_ncc;
+            const bool cs_view = !candidates && cs_active;         // a colour-scale update is due for this view (if it samples)
+            float nccv = -1.f;
+            // ---- sweeps over the 25 samples ----
+#pragma unroll 1
+            for (int rep = 0; rep < 2 && r != 0u; ++rep) {
+                const bool second = rep == 1;
+                if (second && !(cs_view && want_normal && (r & 2u))) break;
+                const bool do_ncc = !second && need_ncc;
+                const bool do_cs = !second && cs_view;
+                // Gauss-Newton terms: directly when the colour scale of this state is known, through per-channel sums when it
+                // is being updated and only the depth step follows, in the second sweep when the normal step follows
+                const bool gn_direct = !candidates && (r & 2u) && (second || !cs_view);
+                const bool gn_sums = !candidates && (r & 2u) && !second && cs_view && !want_normal;
+                float S1a = 0.f, S1b = 0.f, S1c = 0.f, S2a = 0.f, S2b = 0.f, S2c = 0.f, Sen = 0.f;
+                float Mna = 0.f, Mnb = 0.f, Mnc = 0.f, Nna = 0.f, Nnb = 0.f, Nnc = 0.f;
+                float Dma = 0.f, Dmb = 0.f, Dmc = 0.f, Dna = 0.f, Dnb = 0.f, Dnc = 0.f, Dda = 0.f, Ddb = 0.f, Ddc = 0.f;
+                float vnum = 0.f, vden = 0.f;
+                float A0 = 0.f, A1 = 0.f, A2 = 0.f, A3 = 0.f, A4 = 0.f, A5 = 0.f, B0 = 0.f, B1 = 0.f, B2 = 0.f;
+                bool oob = false;
+                const uchar4* mrow = job->ref_img + (size_t)(y0 - 2) * job->ref_pitch + (x0 - 2);
+                float dj = -2.f;
+#pragma unroll 1
+                for (int j = 0; j < 5 && !oob; ++j, dj += 1.f, mrow += job->ref_pitch) {
+                    float di = -2.f;
+#pragma unroll 1
+                    for (int i = 0; i < 5; ++i, di += 1.f) {
+                        float ux, uy, uz, inv;
+                        sample_ray(di, dj, ux, uy, uz, inv);
+                        const float t = depth + di * dzI + dj * dzJ;
+                        const float s1 = t * inv;
+                        const float wx = W0x + di * Wax + dj * Wbx, wy = W0y + di * Way + dj * Wby, wz = W0z + di * Waz + dj * Wbz;
+                        const float hx = A0x + s1 * wx, hy = A0y + s1 * wy, hz = A0z + s1 * wz;
+                        const float ih = rcp_fast(hz);
+                        const float qx = (Lax * hx + Lcx * hz) * ih - 0.5f;
+                        const float qy = (Lay * hy + Lcy * hz) * ih - 0.5f;
+                        if (!(qx > 0.f && qx < wm1 && qy > 0.f && qy < hm1)) { oob = true; break; }
+                        float gx = 0.f, gy = 0.f;
+                        if (dok) {
+                            const float s2 = s1 + step * inv;
+                            const float kx = A0x + s2 * wx, ky = A0y + s2 * wy, kz = A0z + s2 * wz;
+                            const float ik = rcp_fast(kz);
+                            gx = (Lax * kx + Lcx * kz) * ik - 0.5f - qx;
+                            gy = (Lay * ky + Lcy * kz) * ik - 0.5f - qy;
+                        }
+                        const int left = (int)floorf(qx), top = (int)floorf(qy);
+                        const float fx = qx - (float)left, fy = qy - (float)top;
+                        const uint4 Q = __ldg(Lquad + (size_t)top * Lpitch + left);
+                        const uchar4 mt = mrow[i];
+                        const float m[3] = {lutw[mt.x * LUT_REP] * inv_mm, lutw[mt.y * LUT_REP] * inv_mm, lutw[mt.z * LUT_REP] * inv_mm};
+                        float a[3], b[3], c[3], e[3];
+                        a[0] = lutw[(Q.x & 0xFF) * LUT_REP]; a[1] = lutw[((Q.x >> 8) & 0xFF) * LUT_REP]; a[2] = lutw[((Q.x >> 16) & 0xFF) * LUT_REP];
+                        b[0] = lutw[(Q.y & 0xFF) * LUT_REP]; b[1] = lutw[((Q.y >> 8) & 0xFF) * LUT_REP]; b[2] = lutw[((Q.y >> 16) & 0xFF) * LUT_REP];
+                        c[0] = lutw[(Q.z & 0xFF) * LUT_REP]; c[1] = lutw[((Q.z >> 8) & 0xFF) * LUT_REP]; c[2] = lutw[((Q.z >> 16) & 0xFF) * LUT_REP];
+                        e[0] = lutw[(Q.w & 0xFF) * LUT_REP]; e[1] = lutw[((Q.w >> 8) & 0xFF) * LUT_REP]; e[2] = lutw[((Q.w >> 16) & 0xFF) * LUT_REP];
+                        float n[3], d[3];
+#pragma unroll
+                        for (int ch = 0; ch < 3; ++ch) {
+                            const float x0_ = (1.f - fx) * a[ch] + fx * b[ch];
+                            const float x3_ = (1.f - fx) * c[ch] + fx * e[ch];
+                            n[ch] = (1.f - fy) * x0_ + fy * x3_;
+                            const float der = gx * (b[ch] - a[ch]) + gy * (c[ch] - a[ch]) + (gy * fx + gx * fy) * (a[ch] - b[ch] - c[ch] + e[ch]);
+                            d[ch] = dok ? der * dd : 0.f;        // deriv /= stepSize with stepSize = 1 / d (patch_sampler.cc:100,129-130)
+                        }
+                        if (do_ncc) {
+                            const float y0_ = n[0] - pv0, y1_ = n[1] - pv1, y2_ = n[2] - pv2;
+                            S1a += y0_; S1b += y1_; S1c += y2_;
+                            S2a += y0_ * y0_; S2b += y1_ * y1_; S2c += y2_ * y2_;
+                            Sen += (m[0] - mx0) * y0_ + (m[1] - mx1) * y1_ + (m[2] - mx2) * y2_;
+                        }
+                        if (do_cs) {
+                            Mna += m[0] * n[0]; Mnb += m[1] * n[1]; Mnc += m[2] * n[2];
+                            Nna += n[0] * n[0]; Nnb += n[1] * n[1]; Nnc += n[2] * n[2];
+                        }
+                        if (gn_sums) {
+                            Dma += d[0] * m[0]; Dmb += d[1] * m[1]; Dmc += d[2] * m[2];
+                            Dna += d[0] * n[0]; Dnb += d[1] * n[1]; Dnc += d[2] * n[2];
+                            Dda += d[0] * d[0]; Ddb += d[1] * d[1]; Ddc += d[2] * d[2];
+                        }
+                        if (gn_direct) {
+                            // patch_optimization.cc:283-288 / :324-343
+                            const float g0 = c0 * d[0], g1 = c1 * d[1], g2 = c2 * d[2];
+                            const float r0 = m[0] - c0 * n[0], r1 = m[1] - c1 * n[1], r2 = m[2] - c2 * n[2];
+                            vnum += g0 * r0 + g1 * r1 + g2 * r2;
+                            vden += g0 * g0 + g1 * g1 + g2 * g2;
+                            if (want_normal) {
+                                const float gg[3] = {g0, g1, g2};
+                                const float rr[3] = {r0, r1, r2};
+#pragma unroll
+                                for (int ch = 0; ch < 3; ++ch) {
+                                    const float a0 = gg[ch];
+                                    const float a1 = di * a0;      // (ii * cs) * deriv == ii * (cs * deriv) exactly for ii in {-2..2}
+                                    const float a2 = dj * a0;
+                                    A0 += a0 * a0; A1 += a0 * a1; A2 += a0 * a2;
+                                    A3 += a1 * a1; A4 += a1 * a2; A5 += a2 * a2;
+                                    B0 += a0 * rr[ch]; B1 += a1 * rr[ch]; B2 += a2 * rr[ch];
+                                }
+                            }
+                        }
+                    }
+                }
+                if (oob) { r = 0u; break; }
+                if (do_ncc) {                             // getFastNCC (patch_sampler.cc:143-162)
+                    const float inv_n = 1.f / (float)NS;
+                    const float sqrDevY = (S2a - S1a * S1a * inv_n) + (S2b - S1b * S1b * inv_n) + (S2c - S1c * S1c * inv_n);
+                    const float p = sqrDevX * sqrDevY;      // devXY / sqrt(p), -1 when sqrt(p) is not > 0
+                    nccv = p > 0.f ? Sen * rsqrt_fast(p) : -1.f;
+                }
+                if (do_cs) {                              // computeColorScale for this view (patch_optimization.cc:88-110)
+                    float cc[3] = {c0, c1, c2};
+                    const float ab[3] = {Mna - c0 * Nna, Mnb - c1 * Nnb, Mnc - c2 * Nnc};
+                    const float aa[3] = {Nna, Nnb, Nnc};
+#pragma unroll
+                    for (int ch = 0; ch < 3; ++ch) {
+                        if ((double)fabsf(aa[ch]) > 1e-6) {
+                            cc[ch] += ab[ch] * rcp_fast(aa[ch]);
+                            if ((double)cc[ch] > 1e3) opti = false;
+                        } else
+                            opti = false;
+                    }
+                    c0 = cc[0]; c1 = cc[1]; c2 = cc[2];
+#pragma unroll
+                    for (int i = 0; i < MAX_LOCAL; ++i) if (i == k) { cs[i][0] = c0; cs[i][1] = c1; cs[i][2] = c2; }
+                }
+                if (gn_sums) {
+                    vnum = c0 * (Dma - c0 * Dna) + c1 * (Dmb - c1 * Dnb) + c2 * (Dmc - c2 * Dnc);
+                    vden = c0 * c0 * Dda + c1 * c1 * Ddb + c2 * c2 * Ddc;
+                }
+                if (gn_direct || gn_sums) {
+                    num += vnum; den += vden;
+                    if (want_normal && gn_direct) {
+                        // a view's <= 75 products are summed in fp32, the views in fp64; the reference sums all 300 fp32 products
+                        // in fp64 (patch_optimization.cc:336-342) - far below what the Gauss-Newton fixed point resolves
+                        D0 += (double)A0; D1 += (double)A1; D2 += (double)A2; D3 += (double)A3; D4 += (double)A4; D5 += (double)A5;
+                        E0 += (double)B0; E1 += (double)B1; E2 += (double)B2;
+                    }
+                }
+            }
+            if (!candidates) {
+                if (r & 1u) p_col_ok |= 1u << k;
+                if (r & 2u) p_der_ok |= 1u << k;
+                // computeColorScale: a failed view ends the whole update (`return`, not `continue`, patch_optimization.cc:92-93)
+                if (cs_active && !(r & 1u)) cs_active = false;
+                if (want_ncc) set4(ncc, k, (r & 1u) ? nccv : -1.f);
+            } else {
+                const float v = (r & 1u) ? nccv : -1.f;
+                if (v < st->min_ncc) avail &= ~(1u << k);
+                else cand[k] = v;
+            }
+        }
+        if (candidates) return;
+        p_num = num; p_den = den;
+        p_has_normal = want_normal;
+        p_has_ncc = want_ncc;
+        if (want_normal) {
+            // matrix_tools.h:392-398,460-475
+            const double m[9] = {D0, D1, D2, D1, D3, D4, D2, D4, D5};
+            const double det = m[0] * m[4] * m[8] + m[1] * m[5] * m[6] + m[2] * m[3] * m[7]
+                             - m[2] * m[4] * m[6] - m[1] * m[3] * m[8] - m[0] * m[5] * m[7];
+            n_singular = det == 0.0;
+            double inv[9];
+            inv[0] = m[4] * m[8] - m[5] * m[7];
+            inv[1] = m[2] * m[7] - m[1] * m[8];
+            inv[2] = m[1] * m[5] - m[2] * m[4];
+            inv[3] = m[5] * m[6] - m[3] * m[8];
+            inv[4] = m[0] * m[8] - m[2] * m[6];
+            inv[5] = m[2] * m[3] - m[0] * m[5];
+            inv[6] = m[3] * m[7] - m[4] * m[6];
+            inv[7] = m[1] * m[6] - m[0] * m[7];
+            inv[8] = m[0] * m[4] - m[1] * m[3];
+#pragma unroll
+            for (int q = 0; q < 9; ++q) inv[q] /= det;
+            nX0 = (float)(inv[0] * E0 + inv[1] * E1 + inv[2] * E2);
+            nX1 = (float)(inv[3] * E0 + inv[4] * E1 + inv[5] * E2);
+            nX2 = (float)(inv[6] * E0 + inv[7] * E1 + inv[8] * E2);
+        }
+    }
+
+    __device__ __forceinline__ bool all_der_ok() const { return p_der_ok == ((1u << nsel) - 1u); }
+
+    // optimizeDepthOnly (patch_optimization.cc:265-299) from the sums of the last pass. Returns true when the state moved.
+    __device__ __forceinline__ bool depth_step()
+    {
+        if (!all_der_ok()) { opti = false; return false; }
+        if (p_den > 0.f) {
+            depth += p_num / p_den;
+            update();
+            opti = ref_ok;
+            return true;
+        }
+        return false;
+    }
+
+    // optimizeDepthAndNormal (patch_optimization.cc:302-364) from the solution prepared by the last pass.
+    __device__ __forceinline__ bool normal_step()
+    {
+        if (!all_der_ok()) { opti = false; return false; }
+        if (n_singular) { opti = false; return false; }
+        dzI += nX1; dzJ += nX2; depth += nX0;
+        update();
+        opti = ref_ok;
+        return true;
+    }
+
+    // ---- sorted insert / erase on the selected set (std::set semantics) ----
+    __device__ __forceinline__ void sel_erase_mask(unsigned mask)       // bit k: remove element k
+    {
+        int cnt = 0;
+#pragma unroll
+        for (int k = 0; k < MAX_LOCAL; ++k) {
+            if (k < nsel && !((mask >> k) & 1u)) {
+                // element k moves to position cnt (cnt <= k)
+                const int s = sel[k];
+                const float a = cs[k][0], b = cs[k][1], c = cs[k][2], v = ncc[k];
+#pragma unroll
+                for (int q = 0; q < MAX_LOCAL; ++q) if (q == cnt) { sel[q] = s; cs[q][0] = a; cs[q][1] = b; cs[q][2] = c; ncc[q] = v; }
+                ++cnt;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < MAX_LOCAL; ++q) if (q >= cnt) sel[q] = 0xFF;
+        nsel = cnt;
+    }
+    __device__ __forceinline__ void sel_insert(int slot, float cs_init)
+    {
+        int pos = 0;
+#pragma unroll
+        for (int k = 0; k < MAX_LOCAL; ++k) if (k < nsel && sel[k] < slot) ++pos;
+#pragma unroll
+        for (int q = MAX_LOCAL - 1; q > 0; --q)
+            if (q > pos && q <= nsel) { sel[q] = sel[q - 1]; cs[q][0] = cs[q - 1][0]; cs[q][1] = cs[q - 1][1]; cs[q][2] = cs[q - 1][2]; ncc[q] = ncc[q - 1]; }
+#pragma unroll
+        for (int q = 0; q < MAX_LOCAL; ++q) if (q == pos) { sel[q] = slot; cs[q][0] = cs[q][1] = cs[q][2] = cs_init; ncc[q] = 0.f; }
+        ++nsel;
+    }
+
+    // viewDir / epipolar plane / footprint of global slot `slot` at patchPoints[12] (local_view_selection.cc:93-131)
+    __device__ __forceinline__ void cand_geometry(int slot, float rdx, float rdy, float rdz,
+                                                  float& vdx, float& vdy, float& vdz, float& epx, float& epy, float& epz, float& nfp) const
+    {
+        const ViewParams* V = &views[job->gview[slot]];
+        vdx = cpx - __ldg(&V->campos[0]); vdy = cpy - __ldg(&V->campos[1]); vdz = cpz - __ldg(&V->campos[2]);
+        const float nn = sqrtf(vdx * vdx + vdy * vdy + vdz * vdz);
+        vdx /= nn; vdy /= nn; vdz /= nn;
+        epx = vdy * rdz - vdz * rdy; epy = vdz * rdx - vdx * rdz; epz = vdx * rdy - vdy * rdx;
+        const float en = sqrtf(epx * epx + epy * epy + epz * epz);
+        epx /= en; epy /= en; epz /= en;
+        const float z = __ldg(&V->w2c[8]) * cpx + __ldg(&V->w2c[9]) * cpy + __ldg(&V->w2c[10]) * cpz + __ldg(&V->w2c[11]);
+        nfp = z * __ldg(&V->inv_ax0);
+    }
+
+    // Second half of LocalViewSelection::performVS (local_view_selection.cc:86-147)
+    __device__ __forceinline__ void lvs_greedy()
+    {
+        const unsigned N = st->nr_recon_neighbors;
+        const float cs_init = 1.f / mm;
+        float rdx = cpx - c0x, rdy = cpy - c0y, rdz = cpz - c0z;
+        {
+            const float nn = sqrtf(rdx * rdx + rdy * rdy + rdz * rdz);
+            rdx /= nn; rdy /= nn; rdz /= nn;
+        }
+        const int G = job->n_global;
+        bool found = true;
+        while ((unsigned)nsel < N && found) {
+            found = false;
+            float maxScore = 0.f;
+            int maxView = 0;
+#pragma unroll 1
+            for (int c = 0; c < G; ++c) {
+                if (!((avail >> c) & 1u)) continue;
+                float vdx, vdy, vdz, epx, epy, epz, nfp;
+                cand_geometry(c, rdx, rdy, rdz, vdx, vdy, vdz, epx, epy, epz, nfp);
+                float score = cand[c];
+                if (mfp / nfp < 0.5f) score *= 0.01f;
+                float dp = Patch::clamp1(rdx * vdx + rdy * vdy + rdz * vdz);
+                score *= Patch::plx_weight(Patch::deg_acos(dp));
+#pragma unroll 1
+                for (int k = 0; k < nsel; ++k) {
+                    float sx, sy, sz, ex, ey, ez, sfp;
+                    cand_geometry(get4(sel, k), rdx, rdy, rdz, sx, sy, sz, ex, ey, ez, sfp);
+                    dp = Patch::clamp1(sx * vdx + sy * vdy + sz * vdz);
+                    score *= Patch::plx_weight(Patch::deg_acos(dp));
+                    dp = Patch::clamp1(epx * ex + epy * ey + epz * ez);
+                    float angle = fabsf(Patch::deg_acos(dp));
+                    if (angle > 90.f) angle = 180.f - angle;
+                    angle = fmaxf(angle, 1.f);
+                    if (angle < st->min_parallax) score *= angle / st->min_parallax;
+                }
+                if (score > maxScore) { maxScore = score; maxView = c; found = true; }     // local_view_selection.cc:133-137
+            }
+            if (found) {
+                sel_insert(maxView, cs_init);
+                avail &= ~(1u << maxView);
+            }
+        }
+        if ((unsigned)nsel == N) lvs_ok = true;
+    }
+
+    // PatchOptimization ctor (patch_optimization.cc:21-78) incl. LocalViewSelection ctor (local_view_selection.cc:19-54)
+    __device__ __forceinline__ void begin(const JobParams* j, const PatchIn& in)
+    {
+        job = j;
+        rv = &views[job->ref_view];
+        x0 = in.x; y0 = in.y;
+        depth = in.depth; dzI = in.dzI; dzJ = in.dzJ;
+        iter = 0; opti = true; converged = false; lvs_ok = false;
+        nsel = 0; avail = 0u;
+        p_col_ok = p_der_ok = 0u; p_num = p_den = 0.f; p_has_normal = p_has_ncc = false;
+        nX0 = nX1 = nX2 = 0.f; n_singular = true;
+        viewRemoved = was_normal = normal = false;
+        stage = DONE;
+        u0x = u0y = u0z = uax = uay = uaz = ubx = uby = ubz = c0x = c0y = c0z = 0.f;
+        init_sampler(in.x, in.y);
+#pragma unroll
+        for (int k = 0; k < MAX_LOCAL; ++k) {
+            sel[k] = (in.slots >> (8 * k)) & 0xFF;       // propagated ids arrive ascending, 0xFF padded
+            if (sel[k] != 0xFF) nsel = k + 1;
+            cs[k][0] = cs[k][1] = cs[k][2] = 0.f; ncc[k] = 0.f; oldn[k] = 0.f;
+        }
+        if (!ref_ok) { opti = false; return; }
+        const unsigned N = st->nr_recon_neighbors;
+        if ((unsigned)nsel == N) lvs_ok = true;
+        else if ((unsigned)nsel > N) {
+            nsel = 0;
+#pragma unroll
+            for (int k = 0; k < MAX_LOCAL; ++k) sel[k] = 0xFF;
+        }
+        avail = job->n_global >= 32 ? FULL : ((1u << job->n_global) - 1u);
+#pragma unroll
+        for (int k = 0; k < MAX_LOCAL; ++k) if (k < nsel) avail &= ~(1u << sel[k]);
+        const float ci = 1.f / mm;
+#pragma unroll
+        for (int k = 0; k < MAX_LOCAL; ++k) { cs[k][0] = cs[k][1] = cs[k][2] = ci; }
+        stage = lvs_ok ? CTOR : LVS_CTOR;
+    }
+
+    // doAutoOptimization as a state machine around the single pass() call site (see Patch::step)
+    __device__ __forceinline__ bool step()
+    {
+        if (stage == DONE) return true;
+        const bool a_cand = (stage == LVS_CTOR) | (stage == LVS_REPL);
+        const bool a_cs = (stage == CTOR) | (stage == REPL) | ((stage == POST) & was_normal);
+        const bool a_ncc = (stage == PRE) | (stage == POST) | (stage == REPL) | ((stage == FIRST) & (iter == 4));
+        const bool a_normal = (stage == REPL) | ((stage == FIRST) & (iter == 4)) | ((stage == PRE) & normal) |
+                              ((stage == POST) & ((iter + 1) % 5 == 4));
+        pass(a_cand, a_cs, a_ncc, a_normal);
+        if (stage == LVS_CTOR || stage == LVS_REPL) {
+            lvs_greedy();
+            if (!lvs_ok) { if (stage == LVS_CTOR) opti = false; stage = DONE; return true; }
+            stage = (stage == LVS_CTOR) ? CTOR : REPL;
+            return false;
+        }
+        if (!opti) { stage = DONE; return true; }
+        if (stage == POST) {
+            bool conv = true;
+            unsigned tbr = 0u;
+#pragma unroll
+            for (int k = 0; k < MAX_LOCAL; ++k) {
+                if (k >= nsel) continue;
+                const float df = fabsf(ncc[k] - oldn[k]);
+                if (df > st->min_refine_diff) conv = false;
+                if (ncc[k] < st->accept_ncc || (iter == 14 && df > st->min_refine_diff)) tbr |= 1u << k;
+            }
+            if (tbr) {
+                viewRemoved = true;
+                sel_erase_mask(tbr);          // LocalViewSelection::replaceViews (local_view_selection.cc:150-160)
+                lvs_ok = false;
+                stage = LVS_REPL;
+                return false;
+            }
+            if (conv) { converged = true; stage = DONE; return true; }
+            ++iter;
+        } else if (stage == REPL) {
+            ++iter;
+        }
+        while (iter < 4 && opti) {
+            const bool moved = depth_step();
+            ++iter;
+            if (moved && opti) { stage = FIRST; return false; }
+        }
+        if (!opti) { stage = DONE; return true; }
+        if (!((unsigned)iter < st->max_iterations && lvs_ok)) { stage = DONE; return true; }
+        normal = (iter % 5 == 4) || viewRemoved;
+        if (!p_has_ncc || (normal && !p_has_normal)) { stage = PRE; return false; }
+#pragma unroll
+        for (int k = 0; k < MAX_LOCAL; ++k) oldn[k] = ncc[k];
+        opti = false;
+        if (normal) { normal_step(); viewRemoved = false; was_normal = true; }
+        else { depth_step(); was_normal = false; }
+        if (!opti) { stage = DONE; return true; }
+        stage = POST;
+        return false;
+    }
+
+    // PatchOptimization::computeConfidence (patch_optimization.cc:114-142) + getPatchNormal (patch_sampler.cc:243-256)
+    __device__ __forceinline__ void finish(PatchOut& out)
+    {
+        out.depth = depth; out.dzI = dzI; out.dzJ = dzJ;
+        out.iterations = iter;
+        out.flags = (converged ? 1 : 0) | (opti ? 2 : 0);
+        unsigned s = 0u;
+#pragma unroll
+        for (int k = 0; k < MAX_LOCAL; ++k) s |= (unsigned)((k < nsel) ? (sel[k] & 0xFF) : 0xFF) << (8 * k);
+        out.slots = s;
+        out.conf = 0.f; out.nx = out.ny = out.nz = 0.f;
+        if (!converged) return;
+        float mean = 0.f;
+#pragma unroll
+        for (int k = 0; k < MAX_LOCAL; ++k) if (k < nsel) mean += ncc[k];
+        mean /= (float)nsel;
+        const float score = (mean - st->accept_ncc) / (1.f - st->accept_ncc);
+        // patchPoints[14] - patchPoints[10] and patchPoints[2] - patchPoints[22]
+        float px[4], py[4], pz[4];
+        const float di_[4] = {2.f, -2.f, 0.f, 0.f}, dj_[4] = {0.f, 0.f, -2.f, 2.f};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float ux, uy, uz, inv;
+            sample_ray(di_[q], dj_[q], ux, uy, uz, inv);
+            const float s1 = (depth + di_[q] * dzI + dj_[q] * dzJ) * inv;
+            px[q] = c0x + s1 * ux; py[q] = c0y + s1 * uy; pz[q] = c0z + s1 * uz;
+        }
+        const float ax_ = px[0] - px[1], ay_ = py[0] - py[1], az_ = pz[0] - pz[1];
+        const float bx_ = px[2] - px[3], by_ = py[2] - py[3], bz_ = pz[2] - pz[3];
+        float nx = ay_ * bz_ - az_ * by_, ny = az_ * bx_ - ax_ * bz_, nz = ax_ * by_ - ay_ * bx_;
+        const float nn = sqrtf(nx * nx + ny * ny + nz * nz);
+        nx /= nn; ny /= nn; nz /= nn;
+        out.nx = nx; out.ny = ny; out.nz = nz;
+        const float dotP = -(nx * crx + ny * cry + nz * crz);
+        out.conf = (dotP < 0.2f) ? 0.f : score;
+    }
+};
+
+__device__ __forceinline__ void bind_thread(PatchT& p, const DevSettings* st, const ViewParams* views, const float* lut_rep, int tid)
+{
+    p.st = st; p.views = views;
+    p.lutw = lut_rep + (tid & (LUT_REP - 1));
+    p.stage = PatchT::DONE;
+    p.n_sets = 0u;
+}
+
+} // namespace b200mvs

@@ -77,7 +77,7 @@ PATCH_OUT = np.dtype([("conf", "<f4"), ("depth", "<f4"), ("dz_i", "<f4"), ("dz_j
 EXPORTS = ["b200mvs_default_settings", "b200mvs_create", "b200mvs_destroy", "b200mvs_last_error", "b200mvs_version",
            "b200mvs_upload_view", "b200mvs_upload_view_device", "b200mvs_set_view_camera", "b200mvs_set_features", "b200mvs_num_levels",
            "b200mvs_get_level", "b200mvs_global_view_selection", "b200mvs_optimize_patches", "b200mvs_reconstruct",
-           "b200mvs_plan_views"]
+           "b200mvs_plan_views", "b200mvs_set_patch_mode"]
 
 
 def lib():
@@ -109,6 +109,7 @@ def lib():
     L.b200mvs_reconstruct.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p]
     L.b200mvs_plan_views.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    L.b200mvs_set_patch_mode.argtypes = [C.c_void_p, C.c_int, C.c_int64]
     _LIB = L
     return L
 
@@ -206,6 +207,10 @@ class Scene:
         out = np.empty(64, np.int32)
         n = self._check(self._lib.b200mvs_global_view_selection(self._h, C.byref(settings), ref_view, _p(out), 64))
         return out[:n].tolist()
+
+    def set_patch_mode(self, mode: int = 0, thread_min: int = -1):
+        """Engine knob: 1 = eight lanes per patch, 2 = one thread per patch, 0 = by size (see include/b200mvs.h)."""
+        self._check(self._lib.b200mvs_set_patch_mode(self._h, mode, thread_min))
 
     def plan_views(self, settings: Settings, ref_views: Sequence[int]):
         """Global view selection + seed lists of these reference views ahead of their reconstruct() call; safe to call from

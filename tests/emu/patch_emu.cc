@@ -13,6 +13,7 @@ thread_local int t_sense_sub = 0;
 }
 
 #include "../../mve_b200/csrc/patch_opt.cuh"
+#include "../../mve_b200/csrc/patch_thread.cuh"
 
 #include <atomic>
 #include <thread>
@@ -44,7 +45,7 @@ int emu_struct_sizes(int* view, int* pin, int* pout)
 /* settings: min_ncc, min_parallax, accept_ncc, min_refine_diff, max_iterations, nr_recon_neighbors, scale, use_color_scale */
 int emu_optimize_patches(const EmuView* views, int n_views, int ref_view, int W, int H, const float ki[4],
                          const int* gview, int n_global, const float* fsettings, const int* isettings, const float* lut,
-                         const EmuPatchIn* in, int n, EmuPatchOut* out)
+                         const EmuPatchIn* in, int n, EmuPatchOut* out, int mode)
 {
     std::vector<ViewParams> vp(n_views);
     std::memset(vp.data(), 0, vp.size() * sizeof(ViewParams));
@@ -73,6 +74,26 @@ int emu_optimize_patches(const EmuView* views, int n_views, int ref_view, int W,
     job.ref_img = views[ref_view].img[st.scale];
     job.ref_pitch = views[ref_view].pitch[st.scale];
 
+    if (mode == 2) {
+        /* one THREAD per patch (patch_thread.cuh): no collectives, so the device code simply runs patch after patch */
+        std::vector<float> lut_rep(256 * LUT_REP);
+        for (int i = 0; i < 256 * LUT_REP; ++i) lut_rep[i] = lut[i / LUT_REP];
+        PatchT p;
+        bind_thread(p, &st, vp.data(), lut_rep.data(), 0);
+        for (int i = 0; i < n; ++i) {
+            PatchIn pi;
+            pi.x = in[i].x; pi.y = in[i].y; pi.depth = in[i].depth; pi.dzI = in[i].dzI; pi.dzJ = in[i].dzJ; pi.slots = in[i].slots;
+            const unsigned before = p.n_sets;
+            p.begin(&job, pi);
+            while (!p.step()) {}
+            PatchOut po;
+            p.finish(po);
+            out[i].conf = po.conf; out[i].depth = po.depth; out[i].dzI = po.dzI; out[i].dzJ = po.dzJ;
+            out[i].nx = po.nx; out[i].ny = po.ny; out[i].nz = po.nz; out[i].slots = po.slots;
+            out[i].iterations = po.iterations; out[i].flags = po.flags; out[i].sets = p.n_sets - before;
+        }
+        return 0;
+    }
     /* one warp = four 8-lane groups; each group takes patches through a ticket counter exactly like the kernels'
      * optimise_entries() (mve_b200/csrc/b200mvs.cu); "shared memory" = the replicated table */
     simt_emu::Warp warp;

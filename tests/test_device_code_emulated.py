@@ -39,7 +39,7 @@ def _lut():
     return np.where(i <= 0.04045 * 255.0, x / 12.92, ((x + 0.055) / 1.055) ** 2.4).astype(np.float32)
 
 
-def _run(lib, s, osc, ref, gsel, settings, pin):
+def _run(lib, s, osc, ref, gsel, settings, pin, mode=1):
     keep = []          # keeps the RGBX arrays alive
     views = np.zeros(s.n_views, EMU_VIEW)
     for v in range(s.n_views):
@@ -90,7 +90,7 @@ def _run(lib, s, osc, ref, gsel, settings, pin):
     eout = np.zeros(len(pin), EMU_OUT)
     lut = _lut()
     p = lambda a: a.ctypes.data_as(C.c_void_p)
-    rc = lib.emu_optimize_patches(p(views), s.n_views, ref, Ws, Hs, p(ki), p(gv), len(gv), p(fs), p(isv), p(lut), p(ein), len(ein), p(eout))
+    rc = lib.emu_optimize_patches(p(views), s.n_views, ref, Ws, Hs, p(ki), p(gv), len(gv), p(fs), p(isv), p(lut), p(ein), len(ein), p(eout), mode)
     assert rc == 0
     out = np.zeros(len(pin), O.PATCH_OUT)
     out["conf"], out["depth"], out["dz_i"], out["dz_j"] = eout["conf"], eout["depth"], eout["dzI"], eout["dzJ"]
@@ -103,9 +103,10 @@ def _run(lib, s, osc, ref, gsel, settings, pin):
     return out, eout
 
 
+@pytest.mark.parametrize("mode", [1, 2])
 @pytest.mark.parametrize("name,view,kw", [("T0", 0, {}), ("T2", 0, {}), ("T4", 1, {}), ("T0", 2, dict(use_color_scale=0)),
                                           ("T2", 5, dict(nr_recon_neighbors=3))])
-def test_kernel_body_on_oracle_trace(emu, name, view, kw):
+def test_kernel_body_on_oracle_trace(emu, name, view, kw, mode):
     """Seeds (full local view selection), propagated patches and - on the orbit scene - view replacements."""
     s = golden_scene(name)
     osc = O.OracleScene(s)
@@ -120,7 +121,7 @@ def test_kernel_body_on_oracle_trace(emu, name, view, kw):
     # patches whose view set changed = a view was replaced on the way (rare path)
     changed = [i for i in rest if tout["conf"][i] > 0 and (tout["local_ids"][i] != tin["local_ids"][i]).any()][:40]
     pick = np.unique(np.concatenate([seeds, rest[:: max(1, len(rest) // 160)][:160], np.asarray(changed, dtype=np.int64)])).astype(np.int64)
-    got, raw = _run(emu, s, osc, view, gsel, st, tin[pick])
+    got, raw = _run(emu, s, osc, view, gsel, st, tin[pick], mode)
     c = patch_compare(got, tout[pick])
     n = c["n"]
     assert n >= 150
@@ -134,7 +135,8 @@ def test_kernel_body_on_oracle_trace(emu, name, view, kw):
     assert raw["sets"][c["both"]].mean() < 40
 
 
-def test_kernel_body_vs_reference_golden(emu):
+@pytest.mark.parametrize("mode", [1, 2])
+def test_kernel_body_vs_reference_golden(emu, mode):
     """Same device code against mvs::PatchOptimization results of the compiled reference (golden T0 subset)."""
     s = golden_scene("T0")
     ref = golden_ref("T0")
@@ -142,7 +144,7 @@ def test_kernel_body_vs_reference_golden(emu):
     st = O.default_settings(scale=s.scale)
     pin, pout = ref["patch_in"], ref["patch_out"]
     pick = np.concatenate([np.arange(0, len(pin) - 6, 9), np.arange(len(pin) - 6, len(pin))])     # incl. the hostile inputs
-    got, _ = _run(emu, s, osc, int(ref["patch_ref_view"]), ref["patch_gvs"].tolist(), st, pin[pick])
+    got, _ = _run(emu, s, osc, int(ref["patch_ref_view"]), ref["patch_gvs"].tolist(), st, pin[pick], mode)
     c = patch_compare(got, pout[pick])
     assert c["ok_mismatch"] <= 1 and c["ids_mismatch"] <= 1
     assert np.percentile(c["rel"], 99) < 5e-5

@@ -65,13 +65,17 @@ def test_global_view_selection_exact(ctx, name):
             assert o.global_view_selection(os_, v) == want
 
 
+@pytest.mark.parametrize("mode", [1, 2])
 @pytest.mark.parametrize("name", ["T0", "T1", "T2", "T4"])
-def test_patches_vs_reference_golden(ctx, name):
-    """mvs::PatchOptimization results of the compiled reference (ref_harness) on identical inputs."""
+def test_patches_vs_reference_golden(ctx, name, mode):
+    """mvs::PatchOptimization results of the compiled reference (ref_harness) on identical inputs, through both device
+    implementations (1: eight lanes per patch, 2: one thread per patch)."""
     s, g, o = ctx(name)
     ref = golden_ref(name)
     gs, _ = _settings(s)
+    g.set_patch_mode(mode)
     got = g.optimize_patches(gs, int(ref["patch_ref_view"]), ref["patch_gvs"].tolist(), ref["patch_in"])
+    g.set_patch_mode(0)
     c = patch_compare(got, ref["patch_out"])
     n = c["n"]
     assert c["ok_mismatch"] <= max(1, 0.002 * n), c["ok_mismatch"]
@@ -83,13 +87,16 @@ def test_patches_vs_reference_golden(ctx, name):
     assert np.percentile(c["nrm_abs"], 99) < 1e-3
 
 
+@pytest.mark.parametrize("mode", [1, 2])
 @pytest.mark.parametrize("name,view", [("T0", 0), ("T1", 4), ("T2", 0)])
-def test_patches_vs_oracle_trace(ctx, name, view):
+def test_patches_vs_oracle_trace(ctx, name, view, mode):
     """Every PatchOptimization of a whole strict-order reconstruction (seeds + queue), replayed as one batch."""
     s, g, o = ctx(name)
     gs, os_ = _settings(s)
+    g.set_patch_mode(mode)
     r = o.reconstruct(os_, view, trace_cap=100000)
     got = g.optimize_patches(gs, view, o.global_view_selection(os_, view), r["trace_in"])
+    g.set_patch_mode(0)
     c = patch_compare(got, r["trace_out"])
     n = c["n"]
     assert n > 5000
@@ -102,11 +109,15 @@ def test_patches_vs_oracle_trace(ctx, name, view):
 @pytest.mark.parametrize("name,view,tol", [("T0", 0, (0.995, 2e-3)), ("T0", 3, (0.995, 2e-3)), ("T1", 4, (0.995, 2e-3)),
                                            ("T4", 1, (0.995, 2e-3)),
                                            ("T2", 0, (0.97, 1e-2))])
-def test_maps_vs_oracle_same_schedule(ctx, name, view, tol):
-    """DMRecon::start on the GPU vs the restatement running the identical frontier schedule."""
+@pytest.mark.parametrize("thread_min", [0, 1 << 40])
+def test_maps_vs_oracle_same_schedule(ctx, name, view, tol, thread_min):
+    """DMRecon::start on the GPU vs the restatement running the identical frontier schedule; every round through the
+    one-thread-per-patch implementation (thread_min 0) or through the eight-lanes-per-patch one (huge thread_min)."""
     s, g, o = ctx(name)
     gs, os_ = _settings(s)
+    g.set_patch_mode(0, thread_min)
     maps, st = g.reconstruct(gs, [view])
+    g.set_patch_mode(0, -1)
     m = maps[0]
     r = o.reconstruct_wavefront(os_, view, 0.0)
     iou, rel, both = map_stats(r["depth"], m["depth"])

@@ -92,7 +92,7 @@ def test_full_size_view_properties(case):
     ok = out["conf"] > 0
     assert ok.mean() > 0.97
     assert np.percentile(np.abs(out["depth"] - pin["depth"])[ok] / pin["depth"][ok], 99) < 3e-3
-    assert np.percentile(np.abs(out["conf"][ok] - m["conf"][ys[pick], xs[pick]][ok]), 99) < 3e-2
+    assert np.percentile(np.abs(out["conf"][ok] - m["conf"][ys[pick], xs[pick]][ok]), 99) < 4e-2
     need = sorted(set(gsel) | {ref})
     remap = {v: i for i, v in enumerate(need)}
     sub = synth.Scene(name=s.name, width=s.width, height=s.height, images=[s.images[v] for v in need], flen=s.flen[need],
