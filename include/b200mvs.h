@@ -204,6 +204,23 @@ int b200mvs_reconstruct(b200mvs_ctx* ctx, const b200mvs_settings* s, int n_refs,
                         b200mvs_maps* maps, b200mvs_progress* progress, b200mvs_stats* stats,
                         int32_t* failed_view_or_null);
 
+/* ---- consumers of the depth maps, on the device.  Stateless: host buffers in, host buffers
+ *      out, `device` = CUDA device ordinal.  Errors: negative code, message from b200mvs_depthmap_last_error(). ---- */
+const char* b200mvs_depthmap_last_error(void);
+/* mve::image::depthmap_confidence_clean (libs/mve/depthmap.cc:118-131): depth = 0 where conf <= 0, in place. */
+int b200mvs_depthmap_confidence_clean(int device, float* depth, const float* conf, int w, int h);
+/* mve::image::depthmap_cleanup (depthmap.cc:25-113): 4-connected islands of depth != 0 smaller than thres pixels are erased. */
+int b200mvs_depthmap_cleanup(int device, const float* depth, int w, int h, int64_t thres, float* out);
+/* mve::geom::depthmap_triangulate (depthmap.cc:196-375, the per-view work of apps/scene2pset/scene2pset.cc:264-328):
+ * vertex ids per pixel (0xFFFFFFFF = none), vertices (pixel_3dpos; transformed by the 4x4 row-major cam_to_world when given,
+ * like mesh_transform), vertex colours (r, g, b, 1 as floats; NULL colour image = none) and faces, all in the reference's
+ * order.  Outputs may be NULL except the counts; capacities in vertices / faces (w*h and 2*(w-1)*(h-1) always suffice). */
+int b200mvs_depthmap_triangulate(int device, const float* depth, int w, int h, const float invproj[9], float dd_factor,
+                                 const float* cam_to_world_or_null, const uint8_t* color_or_null, int color_channels,
+                                 uint32_t* vertex_ids, float* vertices, float* colors, uint32_t* faces,
+                                 uint64_t cap_vertices, uint64_t cap_faces, uint64_t* n_vertices, uint64_t* n_faces,
+                                 double* device_ms_or_null);
+
 #ifdef __cplusplus
 }
 #endif

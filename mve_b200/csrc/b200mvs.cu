@@ -74,7 +74,7 @@ constexpr int HIST_FINE = 8192;                 // confidence bins of the eligib
 constexpr int HIST_COARSE = 64;                 // one coarse bin per 128 fine bins
 constexpr int HIST_PER_JOB = HIST_FINE + HIST_COARSE;
 constexpr int DEFER_BIT = 1 << 27;              // Entry::jobdir flag: below this round's threshold, carried unchanged
-enum Phase { PH_SEED = 0, PH_SELECT = 1, PH_THRESHOLD = 2, PH_PICK = 3, PH_OPT = 4, PH_COMMIT = 5, PH_EXPAND = 6, PH_NUM = 8 };
+enum Phase { PH_SEED = 0, PH_SELECT = 1, PH_THRESHOLD = 2, PH_PICK = 3, PH_OPT = 4, PH_COMMIT = 5, PH_EXPAND = 6, PH_SORT = 7, PH_NUM = 8 };
 enum Stop { ST_RUN = 0, ST_CANCELLED = 2, ST_OVERFLOW = 3 };
 
 struct FrontierCtl {                            // device memory, zeroed before the launch
@@ -82,6 +82,7 @@ struct FrontierCtl {                            // device memory, zeroed before 
     unsigned long long nlist[2];                // entries in list[0] / list[1]
     unsigned long long nrun;                    // winners of the current round
     unsigned long long ticket;                  // next patch of the current optimise phase
+    unsigned long long sort_cursor;             // next free position of run2 while a round is being grouped by tile
     unsigned long long rounds, peak, run_total, barriers;
     unsigned long long ns[PH_NUM];              // %globaltimer time per phase, measured by CTA 0
     int stop;
@@ -123,7 +124,9 @@ struct b200mvs_ctx {
     bool views_dirty = true;
     float* d_lut = nullptr;
     // workspace (grown on demand, reused across calls)
-    DevBuf<Entry> ent_a, ent_b, run_in;
+    DevBuf<Entry> ent_a, ent_b, run_in, run_sorted;
+    DevBuf<unsigned> tile_cnt;
+    DevBuf<unsigned long long> tile_off;
     DevBuf<PatchOut> run_out;
     DevBuf<unsigned char> written;
     DevBuf<unsigned long long> counters;
@@ -597,6 +600,10 @@ __device__ __forceinline__ unsigned long long entry_key(const Entry& e)
 struct FrontierParams {
     Entry* list[2];
     Entry* run;
+    Entry* run2;                                // the round's winners grouped by 16x16 tile (large rounds)
+    unsigned* tile_cnt;                         // [n_tiles] entries per tile, zero between rounds
+    unsigned long long* tile_off;               // [n_tiles] start of the tile's segment in run2
+    long long n_tiles;
     PatchOut* res;
     unsigned char* written;
     unsigned long long cap;
@@ -820,15 +827,45 @@ k_frontier(const FrontierParams P)
         n_run = __ldcg(&ctl->nrun);
         if (lead) ctl->nlist[p] = 0ull;                           // consumed; the round after the next pushes into it
         }
+        // Large rounds run one thread per patch: group the winners by 16x16-pixel tile first, so that the lanes of a warp and the
+        // warps of an SM sample overlapping windows of the neighbour images (L1 / coalescing).  Tiles get contiguous segments of
+        // run2 in arbitrary order: count per tile, one atomic cursor bump per non-empty tile, scatter.
+        const bool by_thread = n_run >= (unsigned long long)P.thread_min;
+        const Entry* run_cur = P.run;
+        if (by_thread && !seed_round && P.n_tiles > 0) {
+            for (size_t i = gtid; i < n_run; i += gthreads) {
+                const Entry e = load_entry(&P.run[i]);
+                const JobParams& J = P.jobs[e.jobdir & 0xFFFFFF];
+                const long long bin = J.tile_base + (long long)(((e.xy >> 16) & 0xFFFF) >> 4) * J.tiles_x + ((e.xy & 0xFFFF) >> 4);
+                atomicAdd(&P.tile_cnt[bin], 1u);
+            }
+            PHASE_END(PH_SORT);
+            for (size_t b = gtid; b < (size_t)P.n_tiles; b += gthreads) {
+                const unsigned c = __ldcg(&P.tile_cnt[b]);
+                if (c) P.tile_off[b] = atomicAdd(&ctl->sort_cursor, (unsigned long long)c);
+            }
+            PHASE_END(PH_SORT);
+            for (size_t i = gtid; i < n_run; i += gthreads) {
+                const Entry e = load_entry(&P.run[i]);
+                const JobParams& J = P.jobs[e.jobdir & 0xFFFFFF];
+                const long long bin = J.tile_base + (long long)(((e.xy >> 16) & 0xFFFF) >> 4) * J.tiles_x + ((e.xy & 0xFFFF) >> 4);
+                // the tile's counter is consumed downwards: it is zero again when the tile's last entry has been placed
+                const unsigned k = atomicSub(&P.tile_cnt[bin], 1u) - 1u;
+                P.run2[__ldcg(&P.tile_off[bin]) + k] = e;
+            }
+            if (lead) ctl->sort_cursor = 0ull;
+            PHASE_END(PH_SORT);
+            run_cur = P.run2;
+        }
         // the PatchOptimizations of the round
-        if (n_run >= (unsigned long long)P.thread_min) {
+        if (by_thread) {
             PatchT1 pt;
             bind_thread(pt, P.st, P.views, smem, (int)threadIdx.x);
-            optimise_entries_t(pt, P.run, P.res, n_run, &ctl->ticket, P.jobs, cnt);
+            optimise_entries_t(pt, run_cur, P.res, n_run, &ctl->ticket, P.jobs, cnt);
         } else {
             PatchT pg;
             bind_thread(pg, P.st, P.views, smem, (int)threadIdx.x);
-            optimise_entries(pg, P.run, P.res, n_run, &ctl->ticket, P.jobs, cnt);
+            optimise_entries(pg, run_cur, P.res, n_run, &ctl->ticket, P.jobs, cnt);
         }
         if (seed_round) {
             PHASE_END(PH_SEED);
@@ -836,7 +873,7 @@ k_frontier(const FrontierParams P)
                 const float c = __ldcg(&P.res[i].conf);
                 if (!(c > 0.f)) continue;
                 atomicAdd(&cnt[C_SEED_OK], 1ull);
-                const Entry e = load_entry(&P.run[i]);
+                const Entry e = load_entry(&run_cur[i]);
                 const JobParams& J = P.jobs[e.jobdir & 0xFFFFFF];
                 const int idx = ((e.xy >> 16) & 0xFFFF) * J.W + (e.xy & 0xFFFF);
                 atomicMax(&J.sel[idx], ((unsigned long long)__float_as_uint(c) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i));
@@ -845,7 +882,7 @@ k_frontier(const FrontierParams P)
             for (size_t i = gtid; i < (size_t)P.n_seeds; i += gthreads) {
                 const float c = __ldcg(&P.res[i].conf);
                 if (!(c > 0.f)) continue;
-                const Entry e = load_entry(&P.run[i]);
+                const Entry e = load_entry(&run_cur[i]);
                 const int j = e.jobdir & 0xFFFFFF;
                 const JobParams& J = P.jobs[j];
                 const int idx = ((e.xy >> 16) & 0xFFFF) * J.W + (e.xy & 0xFFFF);
@@ -869,7 +906,7 @@ k_frontier(const FrontierParams P)
         PHASE_END(PH_OPT);
         // D: commit (dmrecon.cc:377-398).  One winner per pixel, so plain stores.
         for (size_t i = gtid; i < n_run; i += gthreads) {
-            const Entry e = load_entry(&P.run[i]);
+            const Entry e = load_entry(&run_cur[i]);
             const PatchOut r = load_result(&P.res[i]);
             const int j = e.jobdir & 0xFFFFFF;
             const JobParams& J = P.jobs[j];
@@ -887,7 +924,7 @@ k_frontier(const FrontierParams P)
         // E: after ALL commits, push the 4-neighbours of every committed pixel (dmrecon.cc:400-431)
         for (size_t i = gtid; i < n_run; i += gthreads) {
             if (!P.written[i]) continue;
-            const Entry e = load_entry(&P.run[i]);
+            const Entry e = load_entry(&run_cur[i]);
             const PatchOut r = load_result(&P.res[i]);
             const int j = e.jobdir & 0xFFFFFF;
             const JobParams& J = P.jobs[j];
@@ -1187,7 +1224,7 @@ void b200mvs_destroy(b200mvs_ctx* ctx)
         if (S.dev) cudaFree(S.dev);
         if (S.done) cudaEventDestroy(S.done);
     }
-    ctx->ent_a.release(); ctx->ent_b.release(); ctx->run_in.release(); ctx->run_out.release(); ctx->written.release();
+    ctx->ent_a.release(); ctx->ent_b.release(); ctx->run_in.release(); ctx->run_sorted.release(); ctx->tile_cnt.release(); ctx->tile_off.release(); ctx->run_out.release(); ctx->written.release();
     ctx->counters.release(); ctx->d_jobs.release(); ctx->d_settings.release(); ctx->maps.release();
     ctx->ctl.release(); ctx->hist.release(); ctx->thr_bin.release(); ctx->job_cancel.release();
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
@@ -1478,7 +1515,7 @@ int b200mvs_reconstruct(b200mvs_ctx* ctx, const b200mvs_settings* s, int n_refs,
     std::vector<JobParams> jobs(n_refs);
     std::vector<std::vector<int>> gsels(n_refs);
     std::vector<Entry> seeds;
-    size_t total_px = 0;
+    size_t total_px = 0, n_tiles = 0;
     std::vector<size_t> px_off(n_refs);
     // The per-view host work is independent (the reference runs whole DMRecons on OpenMP threads,
     // apps/dmrecon/dmrecon.cc:285): spread it over host threads.
@@ -1525,6 +1562,9 @@ int b200mvs_reconstruct(b200mvs_ctx* ctx, const b200mvs_settings* s, int n_refs,
         if ((rc = make_job(ctx, *s, refs[j], gsels[j], jobs[j]))) return rc;
         px_off[j] = total_px;
         total_px += (size_t)jobs[j].W * jobs[j].H;
+        jobs[j].tiles_x = (jobs[j].W + 15) / 16;
+        jobs[j].tile_base = (long long)n_tiles;
+        n_tiles += (size_t)jobs[j].tiles_x * ((jobs[j].H + 15) / 16);
         for (const Seed& q : seed_lists[j]) {
             Entry e;
             // a seed outside the image fails in the PatchSampler ctor (patch_sampler.cc:47-50); keep it so that the
@@ -1568,6 +1608,10 @@ int b200mvs_reconstruct(b200mvs_ctx* ctx, const b200mvs_settings* s, int n_refs,
     CK(ctx->ent_a.reserve(cap));
     CK(ctx->ent_b.reserve(cap));
     CK(ctx->run_in.reserve(cap));
+    CK(ctx->run_sorted.reserve(cap));
+    CK(ctx->tile_cnt.reserve(n_tiles));
+    CK(ctx->tile_off.reserve(n_tiles));
+    CK(cudaMemsetAsync(ctx->tile_cnt.p, 0, sizeof(unsigned) * n_tiles, st));
     CK(ctx->run_out.reserve(cap));
     CK(ctx->written.reserve(cap));
     CK(ctx->counters.reserve(C_NUM + n_refs));
@@ -1594,6 +1638,8 @@ int b200mvs_reconstruct(b200mvs_ctx* ctx, const b200mvs_settings* s, int n_refs,
     FrontierParams P;
     P.list[0] = ctx->ent_a.p; P.list[1] = ctx->ent_b.p;
     P.run = ctx->run_in.p; P.res = ctx->run_out.p; P.written = ctx->written.p;
+    P.run2 = ctx->run_sorted.p; P.tile_cnt = ctx->tile_cnt.p; P.tile_off = ctx->tile_off.p;
+    P.n_tiles = std::getenv("B200MVS_NO_TILE_SORT") ? 0 : (long long)n_tiles;
     P.cap = cap; P.n_seeds = (int)seeds.size(); P.n_jobs = n_refs;
     P.st = ctx->d_settings.p; P.jobs = ctx->d_jobs.p; P.views = ctx->d_views; P.lut = ctx->d_lut;
     P.counters = ctx->counters.p; P.ctl = ctx->ctl.p; P.hist = ctx->hist.p; P.thr_bin = ctx->thr_bin.p;

@@ -82,10 +82,11 @@ struct JobParams {            // one reference view being reconstructed (DMRecon
     float ki0, ki2, ki4, ki5; // target_level.invproj entries [0],[2],[4],[5]
     const uchar4* ref_img;    // level `scale` of the reference view
     int ref_pitch;
-    int pad;
+    int tiles_x;              // 16x16-pixel tiles per row of the reference level (frontier sort)
     float* depth; float* conf; float* dz; float* normal;
     unsigned* slots;          // 4 x uint8 global slots per pixel (0xFF = none)
     unsigned long long* sel;  // per-pixel selection key of the current frontier round
+    long long tile_base;      // first tile bin of this job
 };
 
 struct PatchIn  { int x, y; float depth, dzI, dzJ; unsigned slots; };   // slots: 4 x uint8, 0xFF padded, ascending

@@ -27,6 +27,7 @@
 #include <cstring>
 #include <fstream>
 #include <iostream>
+#include <iterator>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -38,6 +39,8 @@
 #include "dmrecon/settings.h"
 #include "dmrecon/single_view.h"
 #include "math/octree_tools.h"
+#include "mve/depthmap.h"
+#include "mve/mesh.h"
 #include "mve/scene.h"
 
 #include "mvs_oracle.h"
@@ -210,8 +213,72 @@ static int run_timed(int argc, char** argv)
     return 0;
 }
 
+/* Depth-map consumers of the reference (libs/mve/depthmap.cc) on raw little-endian buffers:
+ *   ref_harness dmops cleanup W H THRES in.f32 out.f32
+ *   ref_harness dmops confclean W H in.f32 conf.f32 out.f32
+ *   ref_harness dmops triangulate W H DD in.f32 COLOR.u8|- CCH  i0 .. i8  OUTPREFIX
+ *       -> OUTPREFIX.vids (uint32 W*H), .verts (float32 V*3, camera coordinates), .faces (uint32 F*3), .colors (float32 V*4) */
+static std::vector<char> read_all(const char* path)
+{
+    std::ifstream in(path, std::ios::binary);
+    return std::vector<char>((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+}
+static void write_all(const std::string& path, const void* p, std::size_t n)
+{
+    std::ofstream out(path, std::ios::binary);
+    out.write(reinterpret_cast<const char*>(p), (std::streamsize)n);
+}
+static int run_dmops(int argc, char** argv)
+{
+    if (argc < 6) return 2;
+    const std::string op = argv[2];
+    const int W = std::atoi(argv[3]), H = std::atoi(argv[4]);
+    auto load_float = [&](const char* path) {
+        mve::FloatImage::Ptr img = mve::FloatImage::create(W, H, 1);
+        std::vector<char> raw = read_all(path);
+        std::memcpy(img->get_data_pointer(), raw.data(), std::min(raw.size(), (std::size_t)W * H * 4));
+        return img;
+    };
+    if (op == "cleanup" && argc >= 8) {
+        mve::FloatImage::Ptr dm = load_float(argv[6]);
+        mve::FloatImage::Ptr out = mve::image::depthmap_cleanup(dm, std::atoll(argv[5]));
+        write_all(argv[7], out->get_data_pointer(), (std::size_t)W * H * 4);
+        return 0;
+    }
+    if (op == "confclean" && argc >= 8) {
+        mve::FloatImage::Ptr dm = load_float(argv[5]);
+        mve::FloatImage::Ptr cm = load_float(argv[6]);
+        mve::image::depthmap_confidence_clean(dm, cm);
+        write_all(argv[7], dm->get_data_pointer(), (std::size_t)W * H * 4);
+        return 0;
+    }
+    if (op == "triangulate" && argc >= 19) {
+        const float dd = (float)std::atof(argv[5]);
+        mve::FloatImage::Ptr dm = load_float(argv[6]);
+        mve::ByteImage::Ptr ci;
+        const int cch = std::atoi(argv[8]);
+        if (std::string(argv[7]) != "-") {
+            ci = mve::ByteImage::create(W, H, cch);
+            std::vector<char> raw = read_all(argv[7]);
+            std::memcpy(ci->get_data_pointer(), raw.data(), std::min(raw.size(), (std::size_t)W * H * cch));
+        }
+        math::Matrix3f invproj;
+        for (int i = 0; i < 9; ++i) invproj[i] = (float)std::atof(argv[9 + i]);
+        mve::Image<unsigned int> vids;
+        mve::TriangleMesh::Ptr mesh = mve::geom::depthmap_triangulate(dm, ci, invproj, dd, &vids);
+        const std::string prefix = argv[18];
+        write_all(prefix + ".vids", vids.get_data_pointer(), (std::size_t)W * H * 4);
+        write_all(prefix + ".verts", mesh->get_vertices().data(), mesh->get_vertices().size() * 12);
+        write_all(prefix + ".faces", mesh->get_faces().data(), mesh->get_faces().size() * 4);
+        write_all(prefix + ".colors", mesh->get_vertex_colors().data(), mesh->get_vertex_colors().size() * 16);
+        return 0;
+    }
+    return 2;
+}
+
 int main(int argc, char** argv)
 {
+    if (argc >= 3 && std::strcmp(argv[1], "dmops") == 0) return run_dmops(argc, argv);
     if (argc >= 2 && std::strcmp(argv[1], "patches") == 0) return run_patches(argc, argv);
     if (argc >= 2 && std::strcmp(argv[1], "timed") == 0) return run_timed(argc, argv);
     std::fprintf(stderr, "usage: ref_harness patches|timed ...\n");

@@ -27,13 +27,13 @@ def build(cfgs):
         print(out)
 
 
-def run_one(steps, workload):
+def run_one(steps, workload, nviews=16):
     import torch
     from mve_b200 import dmrecon, synth
     s = synth.make_scene(workload, device="cuda")
     g = dmrecon.Scene.from_synth(s)
     st = dmrecon.Settings(scale=s.scale, nr_recon_neighbors=s.nr_recon_neighbors)
-    refs = list(range(min(16, s.n_views)))
+    refs = list(range(min(nviews, s.n_views)))
     g.reconstruct(st, refs, download=False)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     ms, opt, filled = [], [], 0
@@ -50,19 +50,19 @@ def main():
     a = sys.argv[1:]
     if a and a[0] == "--build":
         return build(a[1:])
-    if a and a[0] == "--one":
-        return run_one(int(a[1]), a[2])
-    steps, workload = 3, "C2"
+XX
     while a and a[0].startswith("--"):
         if a[0] == "--steps":
             steps = int(a[1]); a = a[2:]
         elif a[0] == "--workload":
             workload = a[1]; a = a[2:]
+        elif a[0] == "--views":
+            nviews = int(a[1]); a = a[2:]
     for lib in a or ["default"]:
         env = dict(os.environ)
         if lib != "default":
             env["B200MVS_LIB"] = os.path.abspath(lib)
-        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--one", str(steps), workload], env=env, capture_output=True, text=True)
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--one", str(steps), workload, str(nviews)], env=env, capture_output=True, text=True)
         print(r.stdout.strip() or r.stderr[-800:], flush=True)
 
 
