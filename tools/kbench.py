@@ -50,7 +50,9 @@ def main():
     a = sys.argv[1:]
     if a and a[0] == "--build":
         return build(a[1:])
-XX
+    if a and a[0] == "--one":
+        return run_one(int(a[1]), a[2], int(a[3]) if len(a) > 3 else 16)
+    steps, workload, nviews = 3, "C2", 16
     while a and a[0].startswith("--"):
         if a[0] == "--steps":
             steps = int(a[1]); a = a[2:]
@@ -58,6 +60,8 @@ XX
             workload = a[1]; a = a[2:]
         elif a[0] == "--views":
             nviews = int(a[1]); a = a[2:]
+        else:
+            raise SystemExit("unknown option " + a[0])
     for lib in a or ["default"]:
         env = dict(os.environ)
         if lib != "default":
