@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "libb200mvs.so")
 SOURCES = [os.path.join(HERE, "csrc", "b200mvs.cu"), os.path.join(HERE, "csrc", "depthmap.cu")]
-DEPS = SOURCES + [os.path.join(HERE, "csrc", "patch_opt.cuh"), os.path.join(HERE, "csrc", "patch_thread.cuh"),
+DEPS = SOURCES + [os.path.join(HERE, "csrc", "patch_opt.cuh"), os.path.join(HERE, "csrc", "patch_thread.cuh"), os.path.join(HERE, "csrc", "patch_warp.cuh"),
                os.path.join(ROOT, "include", "b200mvs.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v"]

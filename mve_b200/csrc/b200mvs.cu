@@ -2,6 +2,7 @@
 // frontier (region growing) orchestration and all CUDA kernels.  sm_100a only; no CPU fallback.
 #include "../../include/b200mvs.h"
 #include "patch_opt.cuh"
+#include "patch_warp.cuh"
 #include "patch_thread.cuh"
 
 #include <algorithm>
@@ -459,7 +460,7 @@ __global__ void k_export_rgb(const uchar4* __restrict__ src, int w, int h, int p
 // kernels: patch optimisation + frontier
 // ------------------------------------------------------------------------------------------------
 #ifndef OPT_TPB
-#define OPT_TPB 256          // threads per CTA of the patch-optimisation kernels (32 patch groups of 8 lanes)
+#define OPT_TPB 256          // threads per CTA of the patch-optimisation kernels
 #endif
 #ifndef OPT_MIN_BLOCKS
 #define OPT_MIN_BLOCKS 2     // CTAs per SM: registers per thread <= 65536 / (OPT_MIN_BLOCKS * OPT_TPB); shared memory 32 KB per CTA
@@ -467,7 +468,7 @@ __global__ void k_export_rgb(const uchar4* __restrict__ src, int w, int h, int p
 constexpr int OPT_WARPS = OPT_TPB / 32;
 // dynamic shared memory of the kernels that optimise patches: the lane-replicated sRGB table
 constexpr size_t OPT_SMEM_BYTES = sizeof(float) * (256 * LUT_REP);
-using PatchT = Patch;        // 8 lanes per patch (latency: small rounds)
+using PatchT = b200mvs::PatchW;    // one warp per patch (latency: small rounds)
 using PatchT1 = b200mvs::PatchT;   // one thread per patch (throughput: large rounds)
 
 __device__ __forceinline__ Entry load_entry(const Entry* p)       // lists are rewritten by other SMs every round: bypass L1
@@ -480,38 +481,29 @@ __device__ __forceinline__ Entry load_entry(const Entry* p)       // lists are r
     return e;
 }
 
-// The PatchOptimizations of list[0..n): every 8-lane group takes entries through the ticket counter until none is left; a
-// group that finishes one fetches the next at once, the other groups of its warp meet it again at the pass() call site
-// inside Patch::step().  PatchOptimization ctor + doAutoOptimization + computeConfidence per entry.
+// The PatchOptimizations of list[0..n): every warp takes entries through the ticket counter until none is left; a warp that
+// finishes one fetches the next at once.  PatchOptimization ctor + doAutoOptimization + computeConfidence per entry.
 __device__ __forceinline__ void optimise_entries(PatchT& p, const Entry* list, PatchOut* res, unsigned long long n,
                                                  unsigned long long* ticket, const JobParams* jobs, unsigned long long* counters)
 {
-    bool have = false;
-    unsigned long long idx = 0ull;
     unsigned opts = 0u;
     for (;;) {
-        if (!have) {
-            unsigned long long w = 0ull;
-            if (p.gl == 0) w = atomicAdd(ticket, 1ull);
-            w = p.gbcast(w, 0);
-            if (w >= n) break;
-            idx = w;
-            const Entry e = load_entry(&list[w]);
-            PatchIn pi;
-            pi.x = e.xy & 0xFFFF; pi.y = (e.xy >> 16) & 0xFFFF;
-            pi.depth = e.depth; pi.dzI = e.dzI; pi.dzJ = e.dzJ; pi.slots = e.slots;
-            p.begin(&jobs[e.jobdir & 0xFFFFFF], pi);
-            have = true;
-            ++opts;
-        }
-        if (p.step()) {
-            PatchOut po;
-            p.finish(po);
-            if (p.gl == 0) res[idx] = po;
-            have = false;
-        }
+        unsigned long long w = 0ull;
+        if (p.lane == 0) w = atomicAdd(ticket, 1ull);
+        w = __shfl_sync(FULL, w, 0);
+        if (w >= n) break;
+        const Entry e = load_entry(&list[w]);
+        PatchIn pi;
+        pi.x = e.xy & 0xFFFF; pi.y = (e.xy >> 16) & 0xFFFF;
+        pi.depth = e.depth; pi.dzI = e.dzI; pi.dzJ = e.dzJ; pi.slots = e.slots;
+        p.begin(&jobs[e.jobdir & 0xFFFFFF], pi);
+        ++opts;
+        while (!p.step()) {}
+        PatchOut po;
+        p.finish(po);
+        if (p.lane == 0) res[w] = po;
     }
-    if (p.gl == 0 && opts) {
+    if (p.lane == 0 && opts) {
         atomicAdd(&counters[C_SETS], (unsigned long long)p.n_sets);
         atomicAdd(&counters[C_OPTS], (unsigned long long)opts);
         p.n_sets = 0u;
@@ -519,8 +511,8 @@ __device__ __forceinline__ void optimise_entries(PatchT& p, const Entry* list, P
 }
 
 // The same for LARGE lists: one thread per entry (patch_thread.cuh).  Lanes that need an entry take consecutive tickets with
-// one atomic per converged subset of the warp; like the groups above, a lane that finishes fetches its next entry at once
-// and meets the other lanes of its warp again at the pass() call site.
+// one atomic per converged subset of the warp; a lane that finishes fetches its next entry at once and meets the other
+// lanes of its warp again at the pass() call site.
 __device__ __forceinline__ void optimise_entries_t(PatchT1& p, const Entry* list, PatchOut* res, unsigned long long n,
                                                    unsigned long long* ticket, const JobParams* jobs, unsigned long long* counters)
 {
@@ -561,10 +553,10 @@ __device__ __forceinline__ void optimise_entries_t(PatchT1& p, const Entry* list
 }
 
 #ifndef OPT_THREAD_MIN
-#define OPT_THREAD_MIN 16384   // lists at least this long are optimised one thread per patch, shorter ones 8 lanes per patch
+#define OPT_THREAD_MIN 16384   // lists at least this long are optimised one thread per patch, shorter ones one warp per patch
 #endif
 
-// A batch of independent PatchOptimizations (b200mvs_optimize_patches).  mode: 0 = by list length, 1 = 8 lanes per patch,
+// A batch of independent PatchOptimizations (b200mvs_optimize_patches).  mode: 0 = by list length, 1 = one warp per patch,
 // 2 = one thread per patch.
 __global__ void __launch_bounds__(OPT_TPB, OPT_MIN_BLOCKS)
 k_optimize(const Entry* __restrict__ in, PatchOut* __restrict__ out, int n, int mode,
@@ -1449,8 +1441,8 @@ int b200mvs_optimize_patches(b200mvs_ctx* ctx, const b200mvs_settings* s, int re
     {
         int rc2 = prepare_kernels(ctx);
         if (rc2) return rc2;
-        const int groups_per_block = OPT_TPB / GROUP;
-        const int grid = std::max(1, std::min((n + groups_per_block - 1) / groups_per_block, ctx->optimize_grid));
+        const int warps_per_block = OPT_TPB / 32;
+        const int grid = std::max(1, std::min((n + warps_per_block - 1) / warps_per_block, ctx->optimize_grid));
         k_optimize<<<grid, OPT_TPB, OPT_SMEM_BYTES, st>>>(ctx->run_in.p, ctx->run_out.p, n, ctx->optimize_mode, ctx->d_settings.p,
                                                           ctx->d_jobs.p, ctx->d_views, ctx->d_lut, ctx->counters.p);
     }

@@ -1,6 +1,6 @@
 // Device-side patch optimisation, THROUGHPUT variant: one THREAD per patch (32 patches per warp).
 //
-// Same function as Patch in patch_opt.cuh - one mvs::PatchOptimization of the reference
+// Same function as PatchW in patch_warp.cuh - one mvs::PatchOptimization of the reference
 // (libs/dmrecon/patch_optimization.cc:21-364 with PatchSampler patch_sampler.cc:19-393, LocalViewSelection
 // local_view_selection.cc:19-160 and mvs_tools.cc:98-199) - organised for large frontier rounds, where there are far more
 // queue entries than lanes on the chip:
@@ -23,7 +23,7 @@
 //     patch_sampler.cc:94-133 instead of two full point transforms.  Same values up to rounding order (<= 2 ulp on pixel
 //     coordinates; measured against the oracle in tests/test_gpu_parity.py and on the CPU in
 //     tests/test_device_code_emulated.py).
-// The state machine (stages, iteration counting, view replacement) is the one of Patch::step() statement for statement.
+// The state machine (stages, iteration counting, view replacement) is the one of PatchW::step() statement for statement.
 #pragma once
 #include "patch_opt.cuh"
 
@@ -168,7 +168,7 @@ struct PatchT {
         compute_points();
     }
 
-    // One pass at the current state (same contract as Patch::pass).
+    // One pass at the current state (same contract as PatchW::pass).
     __device__ __forceinline__ void pass(bool candidates, bool cs_pending, bool want_ncc, bool want_normal)
     {
         float num = 0.f, den = 0.f;
@@ -509,16 +509,16 @@ struct PatchT {
                 cand_geometry(c, rdx, rdy, rdz, vdx, vdy, vdz, epx, epy, epz, nfp);
                 float score = cand[c];
                 if (mfp / nfp < 0.5f) score *= 0.01f;
-                float dp = Patch::clamp1(rdx * vdx + rdy * vdy + rdz * vdz);
-                score *= Patch::plx_weight(Patch::deg_acos(dp));
+                float dp = clamp1(rdx * vdx + rdy * vdy + rdz * vdz);
+                score *= plx_weight(deg_acos(dp));
 #pragma unroll 1
                 for (int k = 0; k < nsel; ++k) {
                     float sx, sy, sz, ex, ey, ez, sfp;
                     cand_geometry(get4(sel, k), rdx, rdy, rdz, sx, sy, sz, ex, ey, ez, sfp);
-                    dp = Patch::clamp1(sx * vdx + sy * vdy + sz * vdz);
-                    score *= Patch::plx_weight(Patch::deg_acos(dp));
-                    dp = Patch::clamp1(epx * ex + epy * ey + epz * ez);
-                    float angle = fabsf(Patch::deg_acos(dp));
+                    dp = clamp1(sx * vdx + sy * vdy + sz * vdz);
+                    score *= plx_weight(deg_acos(dp));
+                    dp = clamp1(epx * ex + epy * ey + epz * ez);
+                    float angle = fabsf(deg_acos(dp));
                     if (angle > 90.f) angle = 180.f - angle;
                     angle = fmaxf(angle, 1.f);
                     if (angle < st->min_parallax) score *= angle / st->min_parallax;
@@ -571,7 +571,7 @@ struct PatchT {
         stage = lvs_ok ? CTOR : LVS_CTOR;
     }
 
-    // doAutoOptimization as a state machine around the single pass() call site (see Patch::step)
+    // doAutoOptimization as a state machine around the single pass() call site (see PatchW::step)
     __device__ __forceinline__ bool step()
     {
         if (stage == DONE) return true;

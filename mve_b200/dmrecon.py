@@ -210,7 +210,7 @@ class Scene:
         return out[:n].tolist()
 
     def set_patch_mode(self, mode: int = 0, thread_min: int = -1):
-        """Engine knob: 1 = eight lanes per patch, 2 = one thread per patch, 0 = by size (see include/b200mvs.h)."""
+        """Engine knob: 1 = one warp per patch, 2 = one thread per patch, 0 = by size (see include/b200mvs.h)."""
         self._check(self._lib.b200mvs_set_patch_mode(self._h, mode, thread_min))
 
     def plan_views(self, settings: Settings, ref_views: Sequence[int]):

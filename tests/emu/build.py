@@ -6,7 +6,9 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "libpatch_emu.so")
 DEPS = [os.path.join(HERE, "patch_emu.cc"), os.path.join(HERE, "simt_emu.h"),
-        os.path.join(os.path.dirname(os.path.dirname(HERE)), "mve_b200", "csrc", "patch_opt.cuh")]
+        os.path.join(os.path.dirname(os.path.dirname(HERE)), "mve_b200", "csrc", "patch_opt.cuh"),
+        os.path.join(os.path.dirname(os.path.dirname(HERE)), "mve_b200", "csrc", "patch_warp.cuh"),
+        os.path.join(os.path.dirname(os.path.dirname(HERE)), "mve_b200", "csrc", "patch_thread.cuh")]
 
 
 def build(force=False):

@@ -13,6 +13,7 @@ thread_local int t_sense_sub = 0;
 }
 
 #include "../../mve_b200/csrc/patch_opt.cuh"
+#include "../../mve_b200/csrc/patch_warp.cuh"
 #include "../../mve_b200/csrc/patch_thread.cuh"
 
 #include <atomic>
@@ -94,13 +95,11 @@ int emu_optimize_patches(const EmuView* views, int n_views, int ref_view, int W,
         }
         return 0;
     }
-    /* one warp = four 8-lane groups; each group takes patches through a ticket counter exactly like the kernels'
-     * optimise_entries() (mve_b200/csrc/b200mvs.cu); "shared memory" = the replicated table */
+    /* one warp per patch (patch_warp.cuh): 32 host threads run the device code lane by lane; "shared memory" = the
+     * replicated table */
     simt_emu::Warp warp;
-    for (int g = 0; g < 4; ++g) warp.sub8[g].bar.n = 8;
     std::vector<float> lut_rep(256 * LUT_REP);
     for (int i = 0; i < 256 * LUT_REP; ++i) lut_rep[i] = lut[i / LUT_REP];
-    std::atomic<int> ticket(0);
     std::vector<std::thread> lanes;
     for (int lane = 0; lane < 32; ++lane) {
         lanes.emplace_back([&, lane]() {
@@ -108,33 +107,20 @@ int emu_optimize_patches(const EmuView* views, int n_views, int ref_view, int W,
             simt_emu::t_lane = lane;
             simt_emu::t_sense_full = 0;
             simt_emu::t_sense_sub = 0;
-            Patch p;
+            PatchW p;
             bind_thread(p, &st, vp.data(), lut_rep.data(), lane);
-            bool have = false;
-            int idx = 0;
-            unsigned sets_before = 0;
-            for (;;) {
-                if (!have) {
-                    int w = 0;
-                    if (p.gl == 0) w = ticket.fetch_add(1);
-                    w = p.gbcast(w, 0);
-                    if (w >= n) break;
-                    idx = w;
-                    PatchIn pi;
-                    pi.x = in[w].x; pi.y = in[w].y; pi.depth = in[w].depth; pi.dzI = in[w].dzI; pi.dzJ = in[w].dzJ; pi.slots = in[w].slots;
-                    sets_before = p.n_sets;
-                    p.begin(&job, pi);
-                    have = true;
-                }
-                if (p.step()) {
-                    PatchOut po;
-                    p.finish(po);
-                    if (p.gl == 0) {
-                        out[idx].conf = po.conf; out[idx].depth = po.depth; out[idx].dzI = po.dzI; out[idx].dzJ = po.dzJ;
-                        out[idx].nx = po.nx; out[idx].ny = po.ny; out[idx].nz = po.nz; out[idx].slots = po.slots;
-                        out[idx].iterations = po.iterations; out[idx].flags = po.flags; out[idx].sets = p.n_sets - sets_before;
-                    }
-                    have = false;
+            for (int i = 0; i < n; ++i) {
+                PatchIn pi;
+                pi.x = in[i].x; pi.y = in[i].y; pi.depth = in[i].depth; pi.dzI = in[i].dzI; pi.dzJ = in[i].dzJ; pi.slots = in[i].slots;
+                const unsigned before = p.n_sets;
+                p.begin(&job, pi);
+                while (!p.step()) {}
+                PatchOut po;
+                p.finish(po);
+                if (lane == 0) {
+                    out[i].conf = po.conf; out[i].depth = po.depth; out[i].dzI = po.dzI; out[i].dzJ = po.dzJ;
+                    out[i].nx = po.nx; out[i].ny = po.ny; out[i].nz = po.nz; out[i].slots = po.slots;
+                    out[i].iterations = po.iterations; out[i].flags = po.flags; out[i].sets = p.n_sets - before;
                 }
             }
         });
