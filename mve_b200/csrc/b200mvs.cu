@@ -617,10 +617,10 @@ struct FrontierParams {
     int topk;                                   // frontier_topk (0 = off)
 };
 
-__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p)
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p)
 {
     unsigned long long v;
-    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ unsigned long long global_timer_ns()
@@ -630,7 +630,10 @@ __device__ __forceinline__ unsigned long long global_timer_ns()
     return t;
 }
 // All CTAs are co-resident (cooperative launch), so a monotone ticket counter is a barrier: the k-th generation is
-// complete when the counter reaches k * gridDim.x.
+// complete when the counter reaches k * gridDim.x.  The wait polls with a RELAXED load: an acquire load in the loop
+// (ld.acquire = LDG + CCTL.IVALL) would invalidate the SM's L1 on every poll and starve the CTAs of the same SM that are
+// still sampling (measured: L1 hit rate 47 % -> profiles/r2_notes.md); one fence after the wait orders the phase.  Data that
+// other SMs write during the kernel is read with ld.cg everywhere, so no L1 invalidation is needed for correctness.
 __device__ __forceinline__ void grid_barrier(unsigned long long* bar)
 {
     __syncthreads();
@@ -639,7 +642,8 @@ __device__ __forceinline__ void grid_barrier(unsigned long long* bar)
         const unsigned long long nb = gridDim.x;
         const unsigned long long t = atomicAdd(bar, 1ull);
         const unsigned long long target = (t / nb + 1ull) * nb;
-        while (ld_acquire_u64(bar) < target) __nanosleep(64);
+        unsigned ns = 32u;
+        while (ld_relaxed_u64(bar) < target) { __nanosleep(ns); if (ns < 1024u) ns <<= 1; }
         __threadfence();
     }
     __syncthreads();
