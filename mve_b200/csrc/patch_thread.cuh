@@ -255,35 +255,58 @@ struct PatchT {
                 float vnum = 0.f, vden = 0.f;
                 float A0 = 0.f, A1 = 0.f, A2 = 0.f, A3 = 0.f, A4 = 0.f, A5 = 0.f, B0 = 0.f, B1 = 0.f, B2 = 0.f;
                 bool oob = false;
-                const uchar4* mrow = job->ref_img + (size_t)(y0 - 2) * job->ref_pitch + (x0 - 2);
-                float dj = -2.f;
+                // The sample loop is software-pipelined: the geometry of sample k+1 is evaluated and its two loads (quad texel
+                // of the neighbour, master texel) are issued BEFORE sample k is processed, so their latency is covered by the
+                // ~150 instructions of table look-ups, interpolation and sums of sample k (an un-pipelined loop stalled on the
+                // first use of each load, profiles/r2_notes.md).
+                const uchar4* mptr = job->ref_img + (size_t)(y0 - 2) * job->ref_pitch + (x0 - 2);
+                const int mskip = job->ref_pitch - 5;
+                float ndi = -2.f, ndj = -2.f;              // offsets of the NEXT sample
+                float nfx = 0.f, nfy = 0.f, ngx = 0.f, ngy = 0.f;
+                uint4 nQ = make_uint4(0u, 0u, 0u, 0u);
+                uchar4 nmt = make_uchar4(0, 0, 0, 0);
+                bool nvalid = false;
+                // geometry + loads of the sample at (ndi, ndj)
+#define B200MVS_STAGE_NEXT() do { \
+                    float ux_, uy_, uz_, inv_; \
+                    sample_ray(ndi, ndj, ux_, uy_, uz_, inv_); \
+                    const float t_ = depth + ndi * dzI + ndj * dzJ; \
+                    const float s1_ = t_ * inv_; \
+                    const float wx_ = W0x + ndi * Wax + ndj * Wbx, wy_ = W0y + ndi * Way + ndj * Wby, wz_ = W0z + ndi * Waz + ndj * Wbz; \
+                    const float hx_ = A0x + s1_ * wx_, hy_ = A0y + s1_ * wy_, hz_ = A0z + s1_ * wz_; \
+                    const float ih_ = rcp_fast(hz_); \
+                    const float qx_ = (Lax * hx_ + Lcx * hz_) * ih_ - 0.5f; \
+                    const float qy_ = (Lay * hy_ + Lcy * hz_) * ih_ - 0.5f; \
+                    nvalid = qx_ > 0.f && qx_ < wm1 && qy_ > 0.f && qy_ < hm1; \
+                    if (nvalid) { \
+                        ngx = 0.f; ngy = 0.f; \
+                        if (dok) { \
+                            const float s2_ = s1_ + step * inv_; \
+                            const float kx_ = A0x + s2_ * wx_, ky_ = A0y + s2_ * wy_, kz_ = A0z + s2_ * wz_; \
+                            const float ik_ = rcp_fast(kz_); \
+                            ngx = (Lax * kx_ + Lcx * kz_) * ik_ - 0.5f - qx_; \
+                            ngy = (Lay * ky_ + Lcy * kz_) * ik_ - 0.5f - qy_; \
+                        } \
+                        const int left_ = (int)floorf(qx_), top_ = (int)floorf(qy_); \
+                        nfx = qx_ - (float)left_; nfy = qy_ - (float)top_; \
+                        nQ = __ldg(Lquad + (size_t)top_ * Lpitch + left_); \
+                        nmt = *mptr; \
+                    } \
+                } while (0)
+                B200MVS_STAGE_NEXT();
 #pragma unroll 1
-                for (int j = 0; j < 5 && !oob; ++j, dj += 1.f, mrow += job->ref_pitch) {
-                    float di = -2.f;
-#pragma unroll 1
-                    for (int i = 0; i < 5; ++i, di += 1.f) {
-                        float ux, uy, uz, inv;
-                        sample_ray(di, dj, ux, uy, uz, inv);
-                        const float t = depth + di * dzI + dj * dzJ;
-                        const float s1 = t * inv;
-                        const float wx = W0x + di * Wax + dj * Wbx, wy = W0y + di * Way + dj * Wby, wz = W0z + di * Waz + dj * Wbz;
-                        const float hx = A0x + s1 * wx, hy = A0y + s1 * wy, hz = A0z + s1 * wz;
-                        const float ih = rcp_fast(hz);
-                        const float qx = (Lax * hx + Lcx * hz) * ih - 0.5f;
-                        const float qy = (Lay * hy + Lcy * hz) * ih - 0.5f;
-                        if (!(qx > 0.f && qx < wm1 && qy > 0.f && qy < hm1)) { oob = true; break; }
-                        float gx = 0.f, gy = 0.f;
-                        if (dok) {
-                            const float s2 = s1 + step * inv;
-                            const float kx = A0x + s2 * wx, ky = A0y + s2 * wy, kz = A0z + s2 * wz;
-                            const float ik = rcp_fast(kz);
-                            gx = (Lax * kx + Lcx * kz) * ik - 0.5f - qx;
-                            gy = (Lay * ky + Lcy * kz) * ik - 0.5f - qy;
-                        }
-                        const int left = (int)floorf(qx), top = (int)floorf(qy);
-                        const float fx = qx - (float)left, fy = qy - (float)top;
-                        const uint4 Q = __ldg(Lquad + (size_t)top * Lpitch + left);
-                        const uchar4 mt = mrow[i];
+                for (int k = 0; k < NS; ++k) {
+                    if (!nvalid) { oob = true; break; }
+                    // the staged sample becomes the current one
+                    const float di = ndi, dj = ndj, fx = nfx, fy = nfy, gx = ngx, gy = ngy;
+                    const uint4 Q = nQ;
+                    const uchar4 mt = nmt;
+                    if (k + 1 < NS) {
+                        ndi += 1.f; ++mptr;
+                        if (ndi > 2.f) { ndi = -2.f; ndj += 1.f; mptr += mskip; }
+                        B200MVS_STAGE_NEXT();
+                    }
+                    {
                         const float m[3] = {lutw[mt.x * LUT_REP] * inv_mm, lutw[mt.y * LUT_REP] * inv_mm, lutw[mt.z * LUT_REP] * inv_mm};
                         float a[3], b[3], c[3], e[3];
                         a[0] = lutw[(Q.x & 0xFF) * LUT_REP]; a[1] = lutw[((Q.x >> 8) & 0xFF) * LUT_REP]; a[2] = lutw[((Q.x >> 16) & 0xFF) * LUT_REP];
@@ -336,6 +359,7 @@ struct PatchT {
                         }
                     }
                 }
+#undef B200MVS_STAGE_NEXT
                 if (oob) { r = 0u; break; }
                 if (do_ncc) {                             // getFastNCC (patch_sampler.cc:143-162)
                     const float inv_n = 1.f / (float)NS;

@@ -33,6 +33,8 @@ struct int4 { int x, y, z, w; };
 struct uint4 { unsigned x, y, z, w; };
 inline int min(int a, int b) { return a < b ? a : b; }
 inline float4 make_float4(float x, float y, float z, float w) { float4 r = {x, y, z, w}; return r; }
+inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { uint4 r = {x, y, z, w}; return r; }
+inline uchar4 make_uchar4(unsigned char x, unsigned char y, unsigned char z, unsigned char w) { uchar4 r = {x, y, z, w}; return r; }
 
 template <typename T> inline T __ldg(const T* p) { return *p; }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
