@@ -642,8 +642,7 @@ __device__ __forceinline__ void grid_barrier(unsigned long long* bar)
         const unsigned long long nb = gridDim.x;
         const unsigned long long t = atomicAdd(bar, 1ull);
         const unsigned long long target = (t / nb + 1ull) * nb;
-        unsigned ns = 32u;
-        while (ld_relaxed_u64(bar) < target) { __nanosleep(ns); if (ns < 1024u) ns <<= 1; }
+        while (ld_relaxed_u64(bar) < target) __nanosleep(64);
         __threadfence();
     }
     __syncthreads();

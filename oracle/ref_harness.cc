@@ -265,7 +265,9 @@ static int run_dmops(int argc, char** argv)
         math::Matrix3f invproj;
         for (int i = 0; i < 9; ++i) invproj[i] = (float)std::atof(argv[9 + i]);
         mve::Image<unsigned int> vids;
-        mve::TriangleMesh::Ptr mesh = mve::geom::depthmap_triangulate(dm, ci, invproj, dd, &vids);
+        /* the colour overload returns before handing out the vertex ids when there is no colour image (depthmap.cc:340-341) */
+        mve::TriangleMesh::Ptr mesh = ci != nullptr ? mve::geom::depthmap_triangulate(dm, ci, invproj, dd, &vids)
+                                                    : mve::geom::depthmap_triangulate(dm, invproj, dd, &vids);
         const std::string prefix = argv[18];
         write_all(prefix + ".vids", vids.get_data_pointer(), (std::size_t)W * H * 4);
         write_all(prefix + ".verts", mesh->get_vertices().data(), mesh->get_vertices().size() * 12);
