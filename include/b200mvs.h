@@ -127,6 +127,8 @@ typedef struct b200mvs_stats {
     uint64_t n_kernel_launches;   /* all kernel launches of the call                            */
     double   ms_optimise_phases;  /* part of ms_patch_kernel spent in the optimise phases (rest: queue bookkeeping + barriers) */
     uint64_t n_grid_barriers;     /* grid-wide barriers executed by the persistent kernel       */
+    double   ms_optimise_thread_phases; /* part of ms_optimise_phases in rounds run one thread per patch       */
+    double   ms_sort_phases;      /* grouping the winners of large rounds by tile               */
 } b200mvs_stats;
 
 /* ---- lifecycle (mvs::DMRecon ctor/dtor, dmrecon.cc:30-87; ImagePyramidCache, image_pyramid.cc:99-160) ---- */

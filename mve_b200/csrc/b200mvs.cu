@@ -75,7 +75,7 @@ constexpr int HIST_FINE = 8192;                 // confidence bins of the eligib
 constexpr int HIST_COARSE = 64;                 // one coarse bin per 128 fine bins
 constexpr int HIST_PER_JOB = HIST_FINE + HIST_COARSE;
 constexpr int DEFER_BIT = 1 << 27;              // Entry::jobdir flag: below this round's threshold, carried unchanged
-enum Phase { PH_SEED = 0, PH_SELECT = 1, PH_THRESHOLD = 2, PH_PICK = 3, PH_OPT = 4, PH_COMMIT = 5, PH_EXPAND = 6, PH_SORT = 7, PH_NUM = 8 };
+enum Phase { PH_SEED = 0, PH_SELECT = 1, PH_THRESHOLD = 2, PH_PICK = 3, PH_OPT = 4, PH_COMMIT = 5, PH_EXPAND = 6, PH_SORT = 7, PH_OPT_THREAD = 8, PH_NUM = 10 };
 enum Stop { ST_RUN = 0, ST_CANCELLED = 2, ST_OVERFLOW = 3 };
 
 struct FrontierCtl {                            // device memory, zeroed before the launch
@@ -898,7 +898,7 @@ k_frontier(const FrontierParams P)
             p = 0;
             continue;
         }
-        PHASE_END(PH_OPT);
+        if (by_thread) PHASE_END(PH_OPT_THREAD); else PHASE_END(PH_OPT);
         // D: commit (dmrecon.cc:377-398).  One winner per pixel, so plain stores.
         for (size_t i = gtid; i < n_run; i += gthreads) {
             const Entry e = load_entry(&run_cur[i]);
@@ -1741,11 +1741,19 @@ int b200mvs_reconstruct(b200mvs_ctx* ctx, const b200mvs_settings* s, int n_refs,
         // the optimise phases inside the persistent kernel, by %globaltimer of CTA 0 between the grid barriers
         double ns_all = 0.0;
         for (int k = 0; k < PH_NUM; ++k) ns_all += (double)h_ctl->ns[k];
-        const double ns_opt = (double)h_ctl->ns[PH_OPT] + (double)h_ctl->ns[PH_SEED];
+        const double ns_opt = (double)h_ctl->ns[PH_OPT] + (double)h_ctl->ns[PH_SEED] + (double)h_ctl->ns[PH_OPT_THREAD];
         stats->ms_patch_kernel = ms_all;
         stats->ms_total_device = ms_all;
         stats->ms_optimise_phases = ns_all > 0.0 ? ms_all * ns_opt / ns_all : 0.0;
         stats->n_grid_barriers = h_ctl->barriers;
+        if (std::getenv("B200MVS_PHASE_LOG")) {
+            static const char* names[PH_NUM] = {"seed", "select", "threshold", "pick", "opt_warp", "commit", "expand", "sort", "opt_thread", "-"};
+            std::fprintf(stderr, "[b200mvs] kernel %.2f ms, %llu rounds, %llu barriers:", ms_all, (unsigned long long)h_ctl->rounds, (unsigned long long)h_ctl->barriers);
+            for (int k = 0; k < PH_NUM; ++k) std::fprintf(stderr, " %s=%.2f", names[k], ns_all > 0.0 ? ms_all * (double)h_ctl->ns[k] / ns_all : 0.0);
+            std::fprintf(stderr, "\n");
+        }
+        stats->ms_optimise_thread_phases = ns_all > 0.0 ? ms_all * (double)h_ctl->ns[PH_OPT_THREAD] / ns_all : 0.0;
+        stats->ms_sort_phases = ns_all > 0.0 ? ms_all * (double)h_ctl->ns[PH_SORT] / ns_all : 0.0;
     }
     if (cancelled) return fail(ctx, B200MVS_ERR_CANCELLED, "reconstruction cancelled");
     return 0;

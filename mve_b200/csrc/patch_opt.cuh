@@ -84,6 +84,15 @@ __device__ __forceinline__ float rcp_fast(float x) { float r; asm("rcp.approx.ft
 __device__ __forceinline__ float rsqrt_fast(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 #endif
 
+// sRGB code value (byte K of `w`) -> linear, through the lane-replicated table in shared memory: entry v of replica r lives at
+// byte offset v * 128 + r * 4, so the offset is (byte << 7) | lane4 - one shift and one fused and-or (mvs_tools.cc:21-95).
+template <int K> __device__ __forceinline__ float lut_k(const float* table, unsigned lane4, unsigned w)
+{
+    static_assert(LUT_REP == 32, "offset arithmetic assumes 32 replicas");
+    const unsigned off = ((K == 0 ? (w << 7) : (w >> (8 * K - 7))) & 0x7F80u) | lane4;
+    return *reinterpret_cast<const float*>(reinterpret_cast<const char*>(table) + off);
+}
+
 // mvs_tools.h:56-69
 __device__ __forceinline__ float plx_weight(float p)
 {

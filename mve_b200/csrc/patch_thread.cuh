@@ -33,7 +33,8 @@ struct PatchT {
     // ---- constants of the thread ----
     const DevSettings* st;
     const ViewParams* views;
-    const float* lutw;         // replicated srgb2lin table + lane: value v of this lane at lutw[v * LUT_REP]
+    const float* lut_tab;      // lane-replicated srgb2lin table in shared memory (lut_k)
+    unsigned lane4;            // 4 * (lane of this thread)
     // ---- constants of the patch ----
     const JobParams* job;
     const ViewParams* rv;
@@ -136,8 +137,8 @@ struct PatchT {
         for (int j = 0; j < 5; ++j) {
 #pragma unroll
             for (int i = 0; i < 5; ++i) {
-                const uchar4 t = row[i];
-                s0 += lutw[t.x * LUT_REP]; s1 += lutw[t.y * LUT_REP]; s2 += lutw[t.z * LUT_REP];
+                const unsigned t = reinterpret_cast<const unsigned*>(row)[i];
+                s0 += lut_k<0>(lut_tab, lane4, t); s1 += lut_k<1>(lut_tab, lane4, t); s2 += lut_k<2>(lut_tab, lane4, t);
             }
             row += job->ref_pitch;
         }
@@ -151,8 +152,8 @@ struct PatchT {
         for (int j = 0; j < 5; ++j) {
 #pragma unroll
             for (int i = 0; i < 5; ++i) {
-                const uchar4 t = row[i];
-                const float e0 = lutw[t.x * LUT_REP] * inv_mm - mx0, e1 = lutw[t.y * LUT_REP] * inv_mm - mx1, e2 = lutw[t.z * LUT_REP] * inv_mm - mx2;
+                const unsigned t = reinterpret_cast<const unsigned*>(row)[i];
+                const float e0 = lut_k<0>(lut_tab, lane4, t) * inv_mm - mx0, e1 = lut_k<1>(lut_tab, lane4, t) * inv_mm - mx1, e2 = lut_k<2>(lut_tab, lane4, t) * inv_mm - mx2;
                 dev += e0 * e0 + e1 * e1 + e2 * e2;
             }
             row += job->ref_pitch;
@@ -264,7 +265,7 @@ struct PatchT {
                 float ndi = -2.f, ndj = -2.f;              // offsets of the NEXT sample
                 float nfx = 0.f, nfy = 0.f, ngx = 0.f, ngy = 0.f;
                 uint4 nQ = make_uint4(0u, 0u, 0u, 0u);
-                uchar4 nmt = make_uchar4(0, 0, 0, 0);
+                unsigned nmt = 0u;
                 bool nvalid = false;
                 // geometry + loads of the sample at (ndi, ndj)
 #define B200MVS_STAGE_NEXT() do { \
@@ -290,7 +291,7 @@ struct PatchT {
                         const int left_ = (int)floorf(qx_), top_ = (int)floorf(qy_); \
                         nfx = qx_ - (float)left_; nfy = qy_ - (float)top_; \
                         nQ = __ldg(Lquad + (size_t)top_ * Lpitch + left_); \
-                        nmt = *mptr; \
+                        nmt = *reinterpret_cast<const unsigned*>(mptr); \
                     } \
                 } while (0)
                 B200MVS_STAGE_NEXT();
@@ -300,19 +301,19 @@ struct PatchT {
                     // the staged sample becomes the current one
                     const float di = ndi, dj = ndj, fx = nfx, fy = nfy, gx = ngx, gy = ngy;
                     const uint4 Q = nQ;
-                    const uchar4 mt = nmt;
+                    const unsigned mt = nmt;
                     if (k + 1 < NS) {
                         ndi += 1.f; ++mptr;
                         if (ndi > 2.f) { ndi = -2.f; ndj += 1.f; mptr += mskip; }
                         B200MVS_STAGE_NEXT();
                     }
                     {
-                        const float m[3] = {lutw[mt.x * LUT_REP] * inv_mm, lutw[mt.y * LUT_REP] * inv_mm, lutw[mt.z * LUT_REP] * inv_mm};
+                        const float m[3] = {lut_k<0>(lut_tab, lane4, mt) * inv_mm, lut_k<1>(lut_tab, lane4, mt) * inv_mm, lut_k<2>(lut_tab, lane4, mt) * inv_mm};
                         float a[3], b[3], c[3], e[3];
-                        a[0] = lutw[(Q.x & 0xFF) * LUT_REP]; a[1] = lutw[((Q.x >> 8) & 0xFF) * LUT_REP]; a[2] = lutw[((Q.x >> 16) & 0xFF) * LUT_REP];
-                        b[0] = lutw[(Q.y & 0xFF) * LUT_REP]; b[1] = lutw[((Q.y >> 8) & 0xFF) * LUT_REP]; b[2] = lutw[((Q.y >> 16) & 0xFF) * LUT_REP];
-                        c[0] = lutw[(Q.z & 0xFF) * LUT_REP]; c[1] = lutw[((Q.z >> 8) & 0xFF) * LUT_REP]; c[2] = lutw[((Q.z >> 16) & 0xFF) * LUT_REP];
-                        e[0] = lutw[(Q.w & 0xFF) * LUT_REP]; e[1] = lutw[((Q.w >> 8) & 0xFF) * LUT_REP]; e[2] = lutw[((Q.w >> 16) & 0xFF) * LUT_REP];
+                        a[0] = lut_k<0>(lut_tab, lane4, Q.x); a[1] = lut_k<1>(lut_tab, lane4, Q.x); a[2] = lut_k<2>(lut_tab, lane4, Q.x);
+                        b[0] = lut_k<0>(lut_tab, lane4, Q.y); b[1] = lut_k<1>(lut_tab, lane4, Q.y); b[2] = lut_k<2>(lut_tab, lane4, Q.y);
+                        c[0] = lut_k<0>(lut_tab, lane4, Q.z); c[1] = lut_k<1>(lut_tab, lane4, Q.z); c[2] = lut_k<2>(lut_tab, lane4, Q.z);
+                        e[0] = lut_k<0>(lut_tab, lane4, Q.w); e[1] = lut_k<1>(lut_tab, lane4, Q.w); e[2] = lut_k<2>(lut_tab, lane4, Q.w);
                         float n[3], d[3];
 #pragma unroll
                         for (int ch = 0; ch < 3; ++ch) {
@@ -694,7 +695,7 @@ struct PatchT {
 __device__ __forceinline__ void bind_thread(PatchT& p, const DevSettings* st, const ViewParams* views, const float* lut_rep, int tid)
 {
     p.st = st; p.views = views;
-    p.lutw = lut_rep + (tid & (LUT_REP - 1));
+    p.lut_tab = lut_rep; p.lane4 = 4u * (unsigned)(tid & (LUT_REP - 1));
     p.stage = PatchT::DONE;
     p.n_sets = 0u;
 }

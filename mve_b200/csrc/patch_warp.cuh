@@ -77,7 +77,8 @@ struct PatchW {
     const JobParams* job;
     const ViewParams* views;
     const ViewParams* rv;
-    const float* lutw;         // replicated srgb2lin table + lane: value v of this lane at lutw[v * LUT_REP]
+    const float* lut_tab;      // lane-replicated srgb2lin table in shared memory (lut_k)
+    unsigned lane4;            // 4 * (lane of this thread)
     int lane;
     bool act;                  // lane < 25
     float fi, fj;              // sample offsets (patch_optimization.cc:56-64)
@@ -173,8 +174,8 @@ struct PatchW {
         crz = __shfl_sync(FULL, rz, CENTER);
         ref_ok = true;
         // master colours
-        const uchar4 t = job->ref_img[(size_t)(y + dj) * job->ref_pitch + (x + di)];
-        m0 = act ? lutw[t.x * LUT_REP] : 0.f; m1 = act ? lutw[t.y * LUT_REP] : 0.f; m2 = act ? lutw[t.z * LUT_REP] : 0.f;
+        const unsigned t = reinterpret_cast<const unsigned*>(job->ref_img)[(size_t)(y + dj) * job->ref_pitch + (x + di)];
+        m0 = act ? lut_k<0>(lut_tab, lane4, t) : 0.f; m1 = act ? lut_k<1>(lut_tab, lane4, t) : 0.f; m2 = act ? lut_k<2>(lut_tab, lane4, t) : 0.f;
         mm = warp_sum(m0 + m1 + m2) / (3.f * NS);
         if (mm < 0.01f || mm > 0.99f) { ref_ok = false; return; }
         m0 /= mm; m1 /= mm; m2 /= mm;
@@ -246,10 +247,10 @@ struct PatchW {
             const int left = (int)floorf(qx), top = (int)floorf(qy);
             const float fx = qx - (float)left, fy = qy - (float)top;
             const uint4 Q = __ldg(L.quad + (size_t)top * L.pitch + left);
-            const float a[3] = {lutw[(Q.x & 0xFF) * LUT_REP], lutw[((Q.x >> 8) & 0xFF) * LUT_REP], lutw[((Q.x >> 16) & 0xFF) * LUT_REP]};
-            const float b[3] = {lutw[(Q.y & 0xFF) * LUT_REP], lutw[((Q.y >> 8) & 0xFF) * LUT_REP], lutw[((Q.y >> 16) & 0xFF) * LUT_REP]};
-            const float c[3] = {lutw[(Q.z & 0xFF) * LUT_REP], lutw[((Q.z >> 8) & 0xFF) * LUT_REP], lutw[((Q.z >> 16) & 0xFF) * LUT_REP]};
-            const float e[3] = {lutw[(Q.w & 0xFF) * LUT_REP], lutw[((Q.w >> 8) & 0xFF) * LUT_REP], lutw[((Q.w >> 16) & 0xFF) * LUT_REP]};
+            const float a[3] = {lut_k<0>(lut_tab, lane4, Q.x), lut_k<1>(lut_tab, lane4, Q.x), lut_k<2>(lut_tab, lane4, Q.x)};
+            const float b[3] = {lut_k<0>(lut_tab, lane4, Q.y), lut_k<1>(lut_tab, lane4, Q.y), lut_k<2>(lut_tab, lane4, Q.y)};
+            const float c[3] = {lut_k<0>(lut_tab, lane4, Q.z), lut_k<1>(lut_tab, lane4, Q.z), lut_k<2>(lut_tab, lane4, Q.z)};
+            const float e[3] = {lut_k<0>(lut_tab, lane4, Q.w), lut_k<1>(lut_tab, lane4, Q.w), lut_k<2>(lut_tab, lane4, Q.w)};
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch) {
                 const float x0 = (1.f - fx) * a[ch] + fx * b[ch];
@@ -635,7 +636,7 @@ __device__ __forceinline__ void bind_thread(PatchW& p, const DevSettings* st, co
 {
     p.st = st; p.views = views;
     p.lane = tid & 31;
-    p.lutw = lut_rep + (p.lane & (LUT_REP - 1));
+    p.lut_tab = lut_rep; p.lane4 = 4u * (unsigned)(p.lane & (LUT_REP - 1));
     p.stage = PatchW::DONE;
     p.n_sets = 0u;
 }

@@ -62,7 +62,8 @@ class Stats(C.Structure):
                 ("n_filled", C.c_uint64), ("n_seeds_processed", C.c_uint64), ("n_seeds_success", C.c_uint64),
                 ("n_entries_peak", C.c_uint64), ("ms_patch_kernel", C.c_double), ("ms_total_device", C.c_double),
                 ("n_patch_launches", C.c_uint64), ("n_kernel_launches", C.c_uint64),
-                ("ms_optimise_phases", C.c_double), ("n_grid_barriers", C.c_uint64)]
+                ("ms_optimise_phases", C.c_double), ("n_grid_barriers", C.c_uint64),
+                ("ms_optimise_thread_phases", C.c_double), ("ms_sort_phases", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -22,6 +22,7 @@
 #include <map>
 #include <memory>
 #include <mutex>
+#include <sstream>
 #include <stdexcept>
 #include <thread>
 #include <vector>
@@ -378,10 +379,14 @@ DMRecon::start()
     progress.queueSize = 0;
     if (rc0 == B200MVS_ERR_CANCELLED || progress.cancelled) { progress.status = RECON_CANCELLED; return; }
     if (rc0 != 0) throw_for(rc0, req.err);
-    if (!settings.quiet)
-        std::cout << "Reconstructed view " << settings.refViewNr << " (batch of all views in flight: " << stats.n_seeds_processed
-                  << " features processed, " << stats.n_seeds_success << " succeeded optimization, " << stats.n_rounds
-                  << " frontier rounds)." << std::endl;
+    if (!settings.quiet) {
+        std::ostringstream line;       // one write: the OpenMP threads of the driver print concurrently
+        line << "Reconstructed view " << settings.refViewNr << " (batch of all views in flight: " << stats.n_seeds_processed
+             << " features processed, " << stats.n_seeds_success << " succeeded optimization, " << stats.n_rounds
+             << " frontier rounds)." << std::endl;
+        std::lock_guard<std::mutex> lk(g_cout);
+        std::cout << line.str() << std::flush;
+    }
 
     progress.status = RECON_SAVING;
     mve::View::Ptr view = mve_views[settings.refViewNr];

@@ -30,7 +30,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(dmrecon.Settings) == 4 * 10 + 4 * 6 + 4 + 4
     assert dmrecon.PATCH_IN.itemsize == 40 and dmrecon.PATCH_OUT.itemsize == 60
     assert C.sizeof(dmrecon.Progress) == 32
-    assert C.sizeof(dmrecon.Stats) == 8 * 13
+    assert C.sizeof(dmrecon.Stats) == 8 * 15
 
 
 def test_default_settings_match_reference():

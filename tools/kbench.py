@@ -36,13 +36,14 @@ def run_one(steps, workload, nviews=16):
     refs = list(range(min(nviews, s.n_views)))
     g.reconstruct(st, refs, download=False)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    ms, opt, filled = [], [], 0
+    ms, opt, filled, thr, srt = [], [], 0, [], []
     for _ in range(steps):
         flush.zero_()
         torch.cuda.synchronize()
         _, stt = g.reconstruct(st, refs, download=False)
         ms.append(stt.ms_total_device); opt.append(stt.ms_optimise_phases); filled = int(stt.n_filled)
-    print(json.dumps(dict(lib=os.environ.get("B200MVS_LIB", "default"), ms=min(ms), ms_all=ms, optimise_ms=min(opt), filled=filled,
+        thr.append(stt.ms_optimise_thread_phases); srt.append(stt.ms_sort_phases)
+    print(json.dumps(dict(lib=os.environ.get("B200MVS_LIB", "default"), ms=min(ms), ms_all=ms, optimise_ms=min(opt), optimise_thread_ms=min(thr), sort_ms=min(srt), filled=filled,
                           rounds=int(stt.n_rounds), n_opt=int(stt.n_opt), sets=int(stt.n_sample_sets))), flush=True)
 
 
