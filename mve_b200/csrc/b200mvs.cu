@@ -83,6 +83,7 @@ struct FrontierCtl {                            // device memory, zeroed before 
     unsigned long long nlist[2];                // entries in list[0] / list[1]
     unsigned long long nrun;                    // winners of the current round
     unsigned long long ticket;                  // next patch of the current optimise phase
+    unsigned long long ticket2;                 // ... of the tail of a large round (warp-per-patch path)
     unsigned long long sort_cursor;             // next free position of run2 while a round is being grouped by tile
     unsigned long long rounds, peak, run_total, barriers;
     unsigned long long ns[PH_NUM];              // %globaltimer time per phase, measured by CTA 0
@@ -553,7 +554,7 @@ __device__ __forceinline__ void optimise_entries_t(PatchT1& p, const Entry* list
 }
 
 #ifndef OPT_THREAD_MIN
-#define OPT_THREAD_MIN 16384   // lists at least this long are optimised one thread per patch, shorter ones one warp per patch
+#define OPT_THREAD_MIN 65536   // lists at least this long are optimised one thread per patch, shorter ones one warp per patch
 #endif
 
 // A batch of independent PatchOptimizations (b200mvs_optimize_patches).  mode: 0 = by list length, 1 = one warp per patch,
@@ -613,6 +614,7 @@ struct FrontierParams {
     volatile int* host_cancel_job;              // [n_jobs], mapped
     int* job_cancel;                            // [n_jobs], device copy refreshed every round
     long long thread_min;                       // rounds with at least this many patches run one thread per patch
+    long long tail_max;                         // at most this many patches at the end of such a round go to the warp-per-patch path
     int band_bins;                              // frontier_band in fine bins (0 = off)
     int topk;                                   // frontier_topk (0 = off)
 };
@@ -663,9 +665,26 @@ __device__ __forceinline__ PatchOut load_result(const PatchOut* p)  // written b
     r.iterations = e.x; r.flags = e.y;
     return r;
 }
+// Warp-aggregated slot allocation: the lanes of a warp that reach this point together take consecutive slots with ONE atomic
+// (the queue bookkeeping appends ~20 M entries per step to three counters; one same-address atomic per entry cost ~20 ms).
+__device__ __forceinline__ unsigned long long take_slot(unsigned long long* counter)
+{
+    const unsigned m = __activemask();
+    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    unsigned long long base = 0ull;
+    if (lane == leader) base = atomicAdd(counter, (unsigned long long)__popc(m));
+    base = __shfl_sync(m, base, leader);
+    return base + (unsigned long long)__popc(m & ((1u << lane) - 1u));
+}
+// the same for a counter per job: lanes with the same job share one atomic
+__device__ __forceinline__ void count_for_job(unsigned long long* per_job, int j)
+{
+    const unsigned m = __match_any_sync(__activemask(), j);
+    if ((int)(threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(&per_job[j], (unsigned long long)__popc(m));
+}
 __device__ __forceinline__ void push_entry(const FrontierParams& P, int q, const Entry& o)
 {
-    const unsigned long long pos = atomicAdd(&P.ctl->nlist[q], 1ull);
+    const unsigned long long pos = take_slot(&P.ctl->nlist[q]);
     if (pos < P.cap) P.list[q][pos] = o; else P.counters[C_OVERFLOW] = 1ull;
 }
 __device__ __forceinline__ void write_pixel(const JobParams& J, int idx, const PatchOut& r)
@@ -811,7 +830,7 @@ k_frontier(const FrontierParams P)
             const int idx = ((e.xy >> 16) & 0xFFFF) * J.W + (e.xy & 0xFFFF);
             const unsigned long long key = entry_key(e);
             if (__ldcg(&J.sel[idx]) == key && atomicCAS(&J.sel[idx], key, 0ull) == key) {
-                const unsigned long long pos = atomicAdd(&ctl->nrun, 1ull);
+                const unsigned long long pos = take_slot(&ctl->nrun);
                 P.run[pos] = e;                                   // |run| <= n_cur <= capacity
             } else
                 push_entry(P, 1 - p, e);
@@ -853,14 +872,23 @@ k_frontier(const FrontierParams P)
             run_cur = P.run2;
         }
         // the PatchOptimizations of the round
+        // Large rounds: one thread per patch, except the last entries, which are kept for the warp-per-patch path - a warp whose
+        // lanes have drained takes them one at a time (latency of one optimisation ~40 us instead of ~300 us), which fills the
+        // tail of the round while the slowest lanes of other warps finish.  Small rounds: one warp per patch throughout.
+        unsigned long long n_thread = 0ull;
         if (by_thread) {
+            unsigned long long n_tail = n_run / 8ull;
+            if (n_tail > (unsigned long long)P.tail_max) n_tail = (unsigned long long)P.tail_max;
+            n_thread = n_run - n_tail;
             PatchT1 pt;
             bind_thread(pt, P.st, P.views, smem, (int)threadIdx.x);
-            optimise_entries_t(pt, run_cur, P.res, n_run, &ctl->ticket, P.jobs, cnt);
-        } else {
+            optimise_entries_t(pt, run_cur, P.res, n_thread, &ctl->ticket, P.jobs, cnt);
+            __syncwarp();
+        }
+        {
             PatchT pg;
             bind_thread(pg, P.st, P.views, smem, (int)threadIdx.x);
-            optimise_entries(pg, run_cur, P.res, n_run, &ctl->ticket, P.jobs, cnt);
+            optimise_entries(pg, run_cur + n_thread, P.res + n_thread, n_run - n_thread, by_thread ? &ctl->ticket2 : &ctl->ticket, P.jobs, cnt);
         }
         if (seed_round) {
             PHASE_END(PH_SEED);
@@ -884,7 +912,7 @@ k_frontier(const FrontierParams P)
                 const unsigned long long key = ((unsigned long long)__float_as_uint(c) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i);
                 if (__ldcg(&J.sel[idx]) != key) continue;
                 J.sel[idx] = 0ull;
-                atomicAdd(&filled[j], 1ull);
+                count_for_job(filled, j);
                 const PatchOut r = load_result(&P.res[i]);
                 write_pixel(J, idx, r);
                 Entry o;
@@ -909,12 +937,12 @@ k_frontier(const FrontierParams P)
             unsigned char w = 0;
             if (!(r.conf == 0.f)) {
                 const float old = __ldcg(&J.conf[idx]);
-                if (old <= 0.f) atomicAdd(&filled[j], 1ull);
+                if (old <= 0.f) count_for_job(filled, j);
                 if (old < r.conf) { write_pixel(J, idx, r); w = 1; }
             }
             P.written[i] = w;
         }
-        if (lead) { ctl->nrun = 0ull; ctl->ticket = 0ull; }
+        if (lead) { ctl->nrun = 0ull; ctl->ticket = 0ull; ctl->ticket2 = 0ull; }
         PHASE_END(PH_COMMIT);
         // E: after ALL commits, push the 4-neighbours of every committed pixel (dmrecon.cc:400-431)
         for (size_t i = gtid; i < n_run; i += gthreads) {
@@ -1641,6 +1669,8 @@ int b200mvs_reconstruct(b200mvs_ctx* ctx, const b200mvs_settings* s, int n_refs,
     P.host = mirror; P.host_filled = m_filled; P.host_cancel_job = m_cancel_job; P.job_cancel = ctx->job_cancel.p;
     P.thread_min = ctx->thread_min >= 0 ? ctx->thread_min : OPT_THREAD_MIN;
     if (const char* e = std::getenv("B200MVS_THREAD_MIN")) P.thread_min = std::atoll(e);      // tuning knob (tools/kbench.py)
+    P.tail_max = 49152;
+    if (const char* e = std::getenv("B200MVS_TAIL_MAX")) P.tail_max = std::atoll(e);
     P.band_bins = s->frontier_band > 0.f ? std::max(1, (int)(s->frontier_band * (float)HIST_FINE)) : 0;
     P.topk = (int)std::min<uint32_t>(s->frontier_topk, 1u << 30);
 
