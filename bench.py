@@ -468,6 +468,26 @@ def _main(real_stdout):
     if world > 1:
         barrier()
 
+    # ---- sub-line: the consumer of the maps, depthmap_triangulate of one result map on the device ----
+    depthmap_ops = None
+    if rank == 0:
+        try:
+            from mve_b200 import depthmap as D
+            dmap = np.ascontiguousarray(out_bufs[0]["depth"])
+            ax = float(max(Ws, Hs))
+            invproj = np.array([1 / ax, 0, -0.5 * Ws / ax, 0, 1 / ax, -0.5 * Hs / ax, 0, 0, 1], np.float32)
+            D.depthmap_triangulate(dmap, invproj, device=local)
+            tri = D.depthmap_triangulate(dmap, invproj, device=local)
+            nv, nf = len(tri["vertices"]), len(tri["faces"])
+            # algorithmic bytes: depth in (4 B/px), vertex ids out (4 B/px), vertices 12 B, faces 12 B each
+            alg = dmap.size * 8 + nv * 12 + nf * 12
+            depthmap_ops = {"op": "depthmap_triangulate (libs/mve/depthmap.cc:196-375) of one %dx%d result map" % (Ws, Hs),
+                            "device_ms": tri["device_ms"], "vertices": nv, "faces": nf,
+                            "algorithmic_GBs": alg / (tri["device_ms"] * 1e-3) / 1e9 if tri["device_ms"] > 0 else None,
+                            "note": "kernels + one scan, device time; a map of this size is launch-latency bound"}
+        except Exception as ex:
+            depthmap_ops = {"error": repr(ex)}
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": 1e3 * elapsed_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -484,7 +504,7 @@ def _main(real_stdout):
                 "clocks": clocks, "gpu_launches": int(launches_total),
                 "e2e": {"value": f_e2e_total / e2e_max, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "steps": e2e_steps, "ms_per_step": 1e3 * e2e_max / e2e_steps},
-                "roofline": roofline, "cpu_baseline": cpu_baseline}
+                "roofline": roofline, "cpu_baseline": cpu_baseline, "depthmap_ops": depthmap_ops}
         print(json.dumps(line), file=real_stdout, flush=True)
     if world > 1:
         dist.destroy_process_group()

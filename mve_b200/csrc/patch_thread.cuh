@@ -295,7 +295,11 @@ struct PatchT {
                     } \
                 } while (0)
                 B200MVS_STAGE_NEXT();
+#ifdef B200MVS_T1_UNROLL2
+#pragma unroll 2
+#else
 #pragma unroll 1
+#endif
                 for (int k = 0; k < NS; ++k) {
                     if (!nvalid) { oob = true; break; }
                     // the staged sample becomes the current one
