@@ -176,8 +176,10 @@ int b200mvs_global_view_selection(b200mvs_ctx* ctx, const b200mvs_settings* s, i
 
 /* Engine knob (no reference counterpart): which of the two device implementations of PatchOptimization runs.
  * mode (b200mvs_optimize_patches): 0 = by batch size, 1 = one warp per patch (low latency), 2 = one thread per patch
- * (throughput).  thread_min (b200mvs_reconstruct): frontier rounds with at least this many patches run one thread per patch;
- * -1 = built-in default, 0 = always, a huge value = never.  Both implementations are checked against the oracle. */
+ * (throughput).  thread_min (b200mvs_reconstruct): in a frontier round, a VIEW with at least this many patches runs them one
+ * thread per patch, a view with fewer one warp per patch (the rule looks at the view alone, so a view's maps do not depend on
+ * which other views share the batch); -1 = built-in default, 0 = always, a huge value = never.  Both implementations are
+ * checked against the oracle. */
 int b200mvs_set_patch_mode(b200mvs_ctx* ctx, int mode, int64_t thread_min);
 
 /* Prepares, on host threads, what DMRecon::start computes before its queue runs - analyzeFeatures, globalViewSelection and

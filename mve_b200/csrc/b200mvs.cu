@@ -85,6 +85,7 @@ struct FrontierCtl {                            // device memory, zeroed before 
     unsigned long long ticket;                  // next patch of the current optimise phase
     unsigned long long ticket2;                 // ... of the tail of a large round (warp-per-patch path)
     unsigned long long sort_cursor;             // next free position of run2 while a round is being grouped by tile
+    unsigned long long small_cursor;            // ... behind the grouped entries, for the views that run one warp per patch
     unsigned long long rounds, peak, run_total, barriers;
     unsigned long long ns[PH_NUM];              // %globaltimer time per phase, measured by CTA 0
     int stop;
@@ -139,6 +140,7 @@ struct b200mvs_ctx {
     DevBuf<unsigned> hist;
     DevBuf<int> thr_bin;
     DevBuf<int> job_cancel;
+    DevBuf<unsigned long long> job_run;
     int frontier_grid = 0;             // CTAs of the cooperative launch (= what fits on the chip)
     int optimize_grid = 0;             // resident CTAs of k_optimize
     long long thread_min = -1;         // reconstruct: rounds with at least this many patches run one thread per patch (-1: default)
@@ -554,7 +556,7 @@ __device__ __forceinline__ void optimise_entries_t(PatchT1& p, const Entry* list
 }
 
 #ifndef OPT_THREAD_MIN
-#define OPT_THREAD_MIN 65536   // lists at least this long are optimised one thread per patch, shorter ones one warp per patch
+#define OPT_THREAD_MIN 8192    // lists at least this long are optimised one thread per patch, shorter ones one warp per patch
 #endif
 
 // A batch of independent PatchOptimizations (b200mvs_optimize_patches).  mode: 0 = by list length, 1 = one warp per patch,
@@ -613,8 +615,8 @@ struct FrontierParams {
     volatile unsigned long long* host_filled;   // [n_jobs], mapped
     volatile int* host_cancel_job;              // [n_jobs], mapped
     int* job_cancel;                            // [n_jobs], device copy refreshed every round
-    long long thread_min;                       // rounds with at least this many patches run one thread per patch
-    long long tail_max;                         // at most this many patches at the end of such a round go to the warp-per-patch path
+    long long thread_min;                       // a view with at least this many patches in a round runs them one thread per patch
+    unsigned long long* job_run;                // [n_jobs] winners of the round per view
     int band_bins;                              // frontier_band in fine bins (0 = off)
     int topk;                                   // frontier_topk (0 = off)
 };
@@ -831,7 +833,8 @@ k_frontier(const FrontierParams P)
             const unsigned long long key = entry_key(e);
             if (__ldcg(&J.sel[idx]) == key && atomicCAS(&J.sel[idx], key, 0ull) == key) {
                 const unsigned long long pos = take_slot(&ctl->nrun);
-                P.run[pos] = e;                                   // |run| <= n_cur <= capacity
+                P.run[pos] = e;
+                count_for_job(P.job_run, e.jobdir & 0xFFFFFF);                                   // |run| <= n_cur <= capacity
             } else
                 push_entry(P, 1 - p, e);
         }
@@ -841,15 +844,33 @@ k_frontier(const FrontierParams P)
         n_run = __ldcg(&ctl->nrun);
         if (lead) ctl->nlist[p] = 0ull;                           // consumed; the round after the next pushes into it
         }
-        // Large rounds run one thread per patch: group the winners by 16x16-pixel tile first, so that the lanes of a warp and the
-        // warps of an SM sample overlapping windows of the neighbour images (L1 / coalescing).  Tiles get contiguous segments of
-        // run2 in arbitrary order: count per tile, one atomic cursor bump per non-empty tile, scatter.
-        const bool by_thread = n_run >= (unsigned long long)P.thread_min;
+        // Which implementation optimises an entry is decided PER VIEW: a view with at least thread_min winners in this round runs
+        // one thread per patch, a view with fewer one warp per patch.  The rule depends on the view alone, so its maps do not
+        // depend on which other views share the batch (the two implementations differ in rounding).  The entries of the
+        // "thread" views are grouped by 16x16-pixel tile first, so that the lanes of a warp and the warps of an SM sample
+        // overlapping windows of the neighbour images (L1 / coalescing): count per tile, one atomic cursor bump per non-empty
+        // tile, scatter; the entries of the other views follow behind them.
+        unsigned long long n_thread = 0ull;
         const Entry* run_cur = P.run;
-        if (by_thread && !seed_round && P.n_tiles > 0) {
+        if (!seed_round && P.n_tiles > 0) {
+            __shared__ unsigned long long s_big;
+            if (threadIdx.x == 0) s_big = 0ull;
+            __syncthreads();
+            unsigned long long mine = 0ull;
+            for (int j = threadIdx.x; j < P.n_jobs; j += blockDim.x) {
+                const unsigned long long c = __ldcg(&P.job_run[j]);
+                if (c >= (unsigned long long)P.thread_min) mine += c;
+            }
+            if (mine) atomicAdd(&s_big, mine);
+            __syncthreads();
+            n_thread = s_big;
+        }
+        if (n_thread > 0ull) {
             for (size_t i = gtid; i < n_run; i += gthreads) {
                 const Entry e = load_entry(&P.run[i]);
-                const JobParams& J = P.jobs[e.jobdir & 0xFFFFFF];
+                const int j = e.jobdir & 0xFFFFFF;
+                if (__ldcg(&P.job_run[j]) < (unsigned long long)P.thread_min) continue;
+                const JobParams& J = P.jobs[j];
                 const long long bin = J.tile_base + (long long)(((e.xy >> 16) & 0xFFFF) >> 4) * J.tiles_x + ((e.xy & 0xFFFF) >> 4);
                 atomicAdd(&P.tile_cnt[bin], 1u);
             }
@@ -861,31 +882,30 @@ k_frontier(const FrontierParams P)
             PHASE_END(PH_SORT);
             for (size_t i = gtid; i < n_run; i += gthreads) {
                 const Entry e = load_entry(&P.run[i]);
-                const JobParams& J = P.jobs[e.jobdir & 0xFFFFFF];
+                const int j = e.jobdir & 0xFFFFFF;
+                if (__ldcg(&P.job_run[j]) < (unsigned long long)P.thread_min) {
+                    P.run2[n_thread + take_slot(&ctl->small_cursor)] = e;
+                    continue;
+                }
+                const JobParams& J = P.jobs[j];
                 const long long bin = J.tile_base + (long long)(((e.xy >> 16) & 0xFFFF) >> 4) * J.tiles_x + ((e.xy & 0xFFFF) >> 4);
                 // the tile's counter is consumed downwards: it is zero again when the tile's last entry has been placed
                 const unsigned k = atomicSub(&P.tile_cnt[bin], 1u) - 1u;
                 P.run2[__ldcg(&P.tile_off[bin]) + k] = e;
             }
-            if (lead) ctl->sort_cursor = 0ull;
+            if (lead) { ctl->sort_cursor = 0ull; ctl->small_cursor = 0ull; }
             PHASE_END(PH_SORT);
             run_cur = P.run2;
         }
+        const bool by_thread = n_thread > 0ull;
         // the PatchOptimizations of the round
-        // Large rounds: one thread per patch, except the last entries, which are kept for the warp-per-patch path - a warp whose
-        // lanes have drained takes them one at a time (latency of one optimisation ~40 us instead of ~300 us), which fills the
-        // tail of the round while the slowest lanes of other warps finish.  Small rounds: one warp per patch throughout.
-        unsigned long long n_thread = 0ull;
         if (by_thread) {
-            unsigned long long n_tail = n_run / 8ull;
-            if (n_tail > (unsigned long long)P.tail_max) n_tail = (unsigned long long)P.tail_max;
-            n_thread = n_run - n_tail;
             PatchT1 pt;
             bind_thread(pt, P.st, P.views, smem, (int)threadIdx.x);
             optimise_entries_t(pt, run_cur, P.res, n_thread, &ctl->ticket, P.jobs, cnt);
             __syncwarp();
         }
-        {
+        if (n_run > n_thread) {
             PatchT pg;
             bind_thread(pg, P.st, P.views, smem, (int)threadIdx.x);
             optimise_entries(pg, run_cur + n_thread, P.res + n_thread, n_run - n_thread, by_thread ? &ctl->ticket2 : &ctl->ticket, P.jobs, cnt);
@@ -943,6 +963,7 @@ k_frontier(const FrontierParams P)
             P.written[i] = w;
         }
         if (lead) { ctl->nrun = 0ull; ctl->ticket = 0ull; ctl->ticket2 = 0ull; }
+        if (blockIdx.x == 0) for (int j = threadIdx.x; j < P.n_jobs; j += blockDim.x) P.job_run[j] = 0ull;
         PHASE_END(PH_COMMIT);
         // E: after ALL commits, push the 4-neighbours of every committed pixel (dmrecon.cc:400-431)
         for (size_t i = gtid; i < n_run; i += gthreads) {
@@ -1249,7 +1270,7 @@ void b200mvs_destroy(b200mvs_ctx* ctx)
     }
     ctx->ent_a.release(); ctx->ent_b.release(); ctx->run_in.release(); ctx->run_sorted.release(); ctx->tile_cnt.release(); ctx->tile_off.release(); ctx->run_out.release(); ctx->written.release();
     ctx->counters.release(); ctx->d_jobs.release(); ctx->d_settings.release(); ctx->maps.release();
-    ctx->ctl.release(); ctx->hist.release(); ctx->thr_bin.release(); ctx->job_cancel.release();
+    ctx->ctl.release(); ctx->hist.release(); ctx->thr_bin.release(); ctx->job_cancel.release(); ctx->job_run.release();
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -1643,6 +1664,8 @@ int b200mvs_reconstruct(b200mvs_ctx* ctx, const b200mvs_settings* s, int n_refs,
     CK(ctx->ctl.reserve(1));
     CK(ctx->thr_bin.reserve(n_refs));
     CK(ctx->job_cancel.reserve(n_refs));
+    CK(ctx->job_run.reserve(n_refs));
+    CK(cudaMemsetAsync(ctx->job_run.p, 0, sizeof(unsigned long long) * n_refs, st));
     if (thresholded) CK(ctx->hist.reserve((size_t)n_refs * HIST_PER_JOB));
     if ((size_t)(C_NUM + n_refs) > 4096) return fail(ctx, B200MVS_ERR_INVALID_ARG, "too many reference views in one batch");
     const DevSettings ds = to_dev(*s);
@@ -1666,11 +1689,9 @@ int b200mvs_reconstruct(b200mvs_ctx* ctx, const b200mvs_settings* s, int n_refs,
     P.cap = cap; P.n_seeds = (int)seeds.size(); P.n_jobs = n_refs;
     P.st = ctx->d_settings.p; P.jobs = ctx->d_jobs.p; P.views = ctx->d_views; P.lut = ctx->d_lut;
     P.counters = ctx->counters.p; P.ctl = ctx->ctl.p; P.hist = ctx->hist.p; P.thr_bin = ctx->thr_bin.p;
-    P.host = mirror; P.host_filled = m_filled; P.host_cancel_job = m_cancel_job; P.job_cancel = ctx->job_cancel.p;
+    P.host = mirror; P.host_filled = m_filled; P.host_cancel_job = m_cancel_job; P.job_cancel = ctx->job_cancel.p; P.job_run = ctx->job_run.p;
     P.thread_min = ctx->thread_min >= 0 ? ctx->thread_min : OPT_THREAD_MIN;
     if (const char* e = std::getenv("B200MVS_THREAD_MIN")) P.thread_min = std::atoll(e);      // tuning knob (tools/kbench.py)
-    P.tail_max = 49152;
-    if (const char* e = std::getenv("B200MVS_TAIL_MAX")) P.tail_max = std::atoll(e);
     P.band_bins = s->frontier_band > 0.f ? std::max(1, (int)(s->frontier_band * (float)HIST_FINE)) : 0;
     P.topk = (int)std::min<uint32_t>(s->frontier_topk, 1u << 30);
 
