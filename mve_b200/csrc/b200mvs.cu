@@ -88,6 +88,7 @@ struct FrontierCtl {                            // device memory, zeroed before 
     unsigned long long small_cursor;            // ... behind the grouped entries, for the views that run one warp per patch
     unsigned long long rounds, peak, run_total, barriers;
     unsigned long long ns[PH_NUM];              // %globaltimer time per phase, measured by CTA 0
+    unsigned long long thread_busy_ns;          // summed busy time of all warps in the one-thread-per-patch phases
     int stop;
     int pad;
 };
@@ -484,6 +485,13 @@ __device__ __forceinline__ Entry load_entry(const Entry* p)       // lists are r
     return e;
 }
 
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 // The PatchOptimizations of list[0..n): every warp takes entries through the ticket counter until none is left; a warp that
 // finishes one fetches the next at once.  PatchOptimization ctor + doAutoOptimization + computeConfidence per entry.
 __device__ __forceinline__ void optimise_entries(PatchT& p, const Entry* list, PatchOut* res, unsigned long long n,
@@ -517,9 +525,11 @@ __device__ __forceinline__ void optimise_entries(PatchT& p, const Entry* list, P
 // one atomic per converged subset of the warp; a lane that finishes fetches its next entry at once and meets the other
 // lanes of its warp again at the pass() call site.
 __device__ __forceinline__ void optimise_entries_t(PatchT1& p, const Entry* list, PatchOut* res, unsigned long long n,
-                                                   unsigned long long* ticket, const JobParams* jobs, unsigned long long* counters)
+                                                   unsigned long long* ticket, const JobParams* jobs, unsigned long long* counters,
+                                                   unsigned long long* exit_sum = nullptr)
 {
     const int lane = threadIdx.x & 31;
+    const unsigned long long t_phase = exit_sum ? global_timer_ns() : 0ull;
     bool have = false;
     unsigned long long idx = 0ull;
     unsigned opts = 0u;
@@ -553,6 +563,8 @@ __device__ __forceinline__ void optimise_entries_t(PatchT1& p, const Entry* list
         atomicAdd(&counters[C_OPTS], (unsigned long long)opts);
         p.n_sets = 0u;
     }
+    __syncwarp();
+    if (lane == 0 && exit_sum) { atomicAdd(exit_sum, global_timer_ns() - t_phase); }     // busy time of this warp in the phase
 }
 
 #ifndef OPT_THREAD_MIN
@@ -626,12 +638,6 @@ __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long
     unsigned long long v;
     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
-}
-__device__ __forceinline__ unsigned long long global_timer_ns()
-{
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
 }
 // All CTAs are co-resident (cooperative launch), so a monotone ticket counter is a barrier: the k-th generation is
 // complete when the counter reaches k * gridDim.x.  The wait polls with a RELAXED load: an acquire load in the loop
@@ -902,7 +908,7 @@ k_frontier(const FrontierParams P)
         if (by_thread) {
             PatchT1 pt;
             bind_thread(pt, P.st, P.views, smem, (int)threadIdx.x);
-            optimise_entries_t(pt, run_cur, P.res, n_thread, &ctl->ticket, P.jobs, cnt);
+            optimise_entries_t(pt, run_cur, P.res, n_thread, &ctl->ticket, P.jobs, cnt, &ctl->thread_busy_ns);
             __syncwarp();
         }
         if (n_run > n_thread) {
@@ -1801,7 +1807,7 @@ int b200mvs_reconstruct(b200mvs_ctx* ctx, const b200mvs_settings* s, int n_refs,
             static const char* names[PH_NUM] = {"seed", "select", "threshold", "pick", "opt_warp", "commit", "expand", "sort", "opt_thread", "-"};
             std::fprintf(stderr, "[b200mvs] kernel %.2f ms, %llu rounds, %llu barriers:", ms_all, (unsigned long long)h_ctl->rounds, (unsigned long long)h_ctl->barriers);
             for (int k = 0; k < PH_NUM; ++k) std::fprintf(stderr, " %s=%.2f", names[k], ns_all > 0.0 ? ms_all * (double)h_ctl->ns[k] / ns_all : 0.0);
-            std::fprintf(stderr, "\n");
+            std::fprintf(stderr, " | thread-phase warp utilisation %.1f %%\n", h_ctl->ns[PH_OPT_THREAD] ? 100.0 * (double)h_ctl->thread_busy_ns / ((double)h_ctl->ns[PH_OPT_THREAD] * (double)(ctx->frontier_grid * OPT_WARPS)) : 0.0);
         }
         stats->ms_optimise_thread_phases = ns_all > 0.0 ? ms_all * (double)h_ctl->ns[PH_OPT_THREAD] / ns_all : 0.0;
         stats->ms_sort_phases = ns_all > 0.0 ? ms_all * (double)h_ctl->ns[PH_SORT] / ns_all : 0.0;
