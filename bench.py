@@ -348,8 +348,8 @@ def _main(real_stdout):
     def step_e2e():
         flush.zero_()
         pending.pop().result()
+        upload_all()                                 # re-registers the views: not while the planner reads them
         pending.append(planner.submit(gscene.plan_views, settings, refs))
-        upload_all()
         _, st = gscene.reconstruct(settings, refs, download=True, out=out_bufs)
         return st
 
