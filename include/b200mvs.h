@@ -225,6 +225,17 @@ int b200mvs_depthmap_triangulate(int device, const float* depth, int w, int h, c
                                  uint64_t cap_vertices, uint64_t cap_faces, uint64_t* n_vertices, uint64_t* n_faces,
                                  double* device_ms_or_null);
 
+/* The per-view work of apps/scene2pset (scene2pset.cc:264-358) in one call: depthmap_triangulate as above plus, per vertex,
+ * the angle-weighted normals of TriangleMesh::recalc_normals (mesh.cc:45-151; normals NULL = skip), the boundary confidences
+ * of depthmap_mesh_confidences(mesh, conf_iterations) (depthmap.cc:497-548; the app uses 4; confidences NULL or 0 = skip) and
+ * the scale values (mean distance to the adjacent vertices of MeshInfo times scale_factor, scene2pset.cc:347-357; NULL = skip). */
+int b200mvs_depthmap_pointset(int device, const float* depth, int w, int h, const float invproj[9], float dd_factor,
+                              const float* cam_to_world_or_null, const uint8_t* color_or_null, int color_channels,
+                              uint32_t* vertex_ids, float* vertices, float* colors, uint32_t* faces,
+                              float* normals, float* confidences, int conf_iterations, float* scales, float scale_factor,
+                              uint64_t cap_vertices, uint64_t cap_faces, uint64_t* n_vertices, uint64_t* n_faces,
+                              double* device_ms_or_null);
+
 #ifdef __cplusplus
 }
 #endif

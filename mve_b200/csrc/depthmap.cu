@@ -281,6 +281,180 @@ __global__ void k_tri_faces(const unsigned char* __restrict__ codes, int w, int 
         ++f;
     }
 }
+
+// ---- per-vertex attributes of the triangulated depth map: what apps/scene2pset adds per view (scene2pset.cc:316-358) ----
+// All of them are functions of a vertex' adjacent faces, which on a depth-map mesh are the <= 8 triangles of the four 2x2
+// blocks around its pixel; visiting those blocks in raster order (and a block's triangles in emission order) enumerates the
+// faces in ascending face id - the order in which the reference accumulates (mesh.cc:45-119, mesh_info.cc:28-33).
+struct AdjFace { unsigned a, b, c, first, second; };
+
+__device__ __forceinline__ int adjacent_faces(const unsigned char* __restrict__ codes, const unsigned* __restrict__ vids, int w, int h,
+                                              int px, int py, unsigned v, AdjFace* out)
+{
+    const int bx[4] = {px - 1, px, px - 1, px}, by[4] = {py - 1, py - 1, py, py}, corner[4] = {3, 2, 1, 0};
+    int n = 0;
+    for (int k = 0; k < 4; ++k) {
+        if (bx[k] < 0 || by[k] < 0 || bx[k] >= w - 1 || by[k] >= h - 1) continue;
+        const size_t bi = (size_t)by[k] * w + bx[k];
+        const unsigned code = codes[bi];
+        for (int j = 0; j < 2; ++j) {
+            const int t = (code >> (4 * j)) & 0xF;
+            if (!t) continue;
+            const int* tv = c_tris[t - 1];
+            int pos = -1;
+            for (int q = 0; q < 3; ++q) if (tv[q] == corner[k]) pos = q;
+            if (pos < 0) continue;
+            unsigned id[3];
+            for (int q = 0; q < 3; ++q) id[q] = vids[bi + (tv[q] & 1) + (size_t)w * (tv[q] >> 1)];
+            AdjFace f;
+            f.a = id[0]; f.b = id[1]; f.c = id[2];
+            f.first = id[(pos + 1) % 3]; f.second = id[(pos + 2) % 3];
+            out[n++] = f;
+        }
+    }
+    (void)v;
+    return n;
+}
+
+__device__ __forceinline__ float clampf(float v, float lo, float hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// MeshInfo::update_vertex (mesh_info.cc:55-163): chains the adjacent faces; returns the class (0 simple, 1 complex, 2 border,
+// 3 unreferenced - MeshInfo::VertexClass) and the adjacent vertices in the reference's order.
+__device__ __forceinline__ int classify_vertex(const AdjFace* faces, int n, unsigned* verts, int* n_verts)
+{
+    *n_verts = 0;
+    if (n == 0) return 3;
+    bool used[8] = {false, false, false, false, false, false, false, false};
+    unsigned sf[17], ss[17];                 // sorted chain as a deque in the middle of an array
+    int lo = 8, hi = 8;
+    sf[8] = faces[0].first; ss[8] = faces[0].second; used[0] = true;
+    int left = n - 1;
+    while (left > 0) {
+        const unsigned front_id = sf[lo], back_id = ss[hi];
+        bool found = false;
+        for (int i = 0; i < n; ++i) {
+            if (used[i]) continue;
+            if (front_id == faces[i].second) { --lo; sf[lo] = faces[i].first; ss[lo] = faces[i].second; used[i] = true; found = true; break; }
+            if (back_id == faces[i].first) { ++hi; sf[hi] = faces[i].first; ss[hi] = faces[i].second; used[i] = true; found = true; break; }
+        }
+        if (!found) break;
+        --left;
+    }
+    if (left > 0) {
+        // complex: unique, ascending list of all adjacent vertices (std::set)
+        unsigned tmp[16];
+        int m = 0;
+        for (int i = 0; i < n; ++i) { tmp[m++] = faces[i].first; tmp[m++] = faces[i].second; }
+        for (int i = 1; i < m; ++i) { const unsigned key = tmp[i]; int j = i - 1; while (j >= 0 && tmp[j] > key) { tmp[j + 1] = tmp[j]; --j; } tmp[j + 1] = key; }
+        int k = 0;
+        for (int i = 0; i < m; ++i) if (i == 0 || tmp[i] != tmp[i - 1]) verts[k++] = tmp[i];
+        *n_verts = k;
+        return 1;
+    }
+    const bool simple = sf[lo] == ss[hi];
+    int k = 0;
+    for (int i = lo; i <= hi; ++i) verts[k++] = sf[i];
+    if (!simple) verts[k++] = ss[hi];
+    *n_verts = k;
+    return simple ? 0 : 2;
+}
+
+__global__ void k_vertex_attributes(const unsigned char* __restrict__ codes, const unsigned* __restrict__ vids, int w, int h,
+                                    const float* __restrict__ verts, float scale_factor,
+                                    float* __restrict__ normals, float* __restrict__ scales, unsigned char* __restrict__ ring)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    const size_t pi = (size_t)y * w + x;
+    const unsigned v = vids[pi];
+    if (ring) ring[pi] = 255;
+    if (v == 0xFFFFFFFFu) return;
+    AdjFace faces[8];
+    const int n = adjacent_faces(codes, vids, w, h, x, y, v, faces);
+    if (normals) {
+        // TriangleMesh::recalc_normals, angle-weighted pseudo normals (mesh.cc:45-151)
+        float nx = 0.f, ny = 0.f, nz = 0.f;
+        for (int i = 0; i < n; ++i) {
+            const float* A = verts + 3 * (size_t)faces[i].a; const float* B = verts + 3 * (size_t)faces[i].b; const float* C = verts + 3 * (size_t)faces[i].c;
+            const float abx = B[0] - A[0], aby = B[1] - A[1], abz = B[2] - A[2];
+            const float bcx = C[0] - B[0], bcy = C[1] - B[1], bcz = C[2] - B[2];
+            const float cax = A[0] - C[0], cay = A[1] - C[1], caz = A[2] - C[2];
+            // fn = ab x (-ca)
+            float fx = aby * (-caz) - abz * (-cay), fy = abz * (-cax) - abx * (-caz), fz = abx * (-cay) - aby * (-cax);
+            const float fnl = sqrtf(fx * fx + fy * fy + fz * fz);
+            if (fnl == 0.0f) continue;
+            fx /= fnl; fy /= fnl; fz /= fnl;
+            const float abl = sqrtf(abx * abx + aby * aby + abz * abz), bcl = sqrtf(bcx * bcx + bcy * bcy + bcz * bcz), cal = sqrtf(cax * cax + cay * cay + caz * caz);
+            float ratio;
+            if (faces[i].a == v) ratio = (abx / abl) * (-cax / cal) + (aby / abl) * (-cay / cal) + (abz / abl) * (-caz / cal);
+            else if (faces[i].b == v) ratio = (-abx / abl) * (bcx / bcl) + (-aby / abl) * (bcy / bcl) + (-abz / abl) * (bcz / bcl);
+            else ratio = (cax / cal) * (-bcx / bcl) + (cay / cal) * (-bcy / bcl) + (caz / cal) * (-bcz / bcl);
+            const float angle = acosf(clampf(ratio, -1.0f, 1.0f));
+            nx += fx * angle; ny += fy * angle; nz += fz * angle;
+        }
+        const float vnl = sqrtf(nx * nx + ny * ny + nz * nz);
+        if (vnl > 0.0f) { nx /= vnl; ny /= vnl; nz /= vnl; }
+        normals[3 * (size_t)v] = nx; normals[3 * (size_t)v + 1] = ny; normals[3 * (size_t)v + 2] = nz;
+    }
+    if (scales || ring) {
+        unsigned adj[16];
+        int na = 0;
+        const int cls = classify_vertex(faces, n, adj, &na);
+        if (ring && cls == 2) ring[pi] = 0;                       // MeshInfo::VERTEX_CLASS_BORDER starts the confidence rings
+        if (scales) {
+            // scene2pset.cc:347-357: mean distance to the adjacent vertices, times the scale factor
+            const float* P0 = verts + 3 * (size_t)v;
+            float sum = 0.f;
+            for (int k = 0; k < na; ++k) {
+                const float* Q = verts + 3 * (size_t)adj[k];
+                const float dx = P0[0] - Q[0], dy = P0[1] - Q[1], dz = P0[2] - Q[2];
+                sum += sqrtf(dx * dx + dy * dy + dz * dz);
+            }
+            sum /= (float)na;
+            scales[v] = sum * scale_factor;
+        }
+    }
+}
+
+// depthmap_mesh_confidences (depthmap.cc:497-548): ring d = vertices at d face-edge hops from a border vertex get d / iterations.
+__global__ void k_conf_ring(const unsigned char* __restrict__ codes, const unsigned* __restrict__ vids, int w, int h,
+                            const unsigned char* __restrict__ ring_in, unsigned char* __restrict__ ring_out, int d)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    const size_t pi = (size_t)y * w + x;
+    unsigned char r = ring_in[pi];
+    const unsigned v = vids[pi];
+    if (v != 0xFFFFFFFFu && r == 255) {
+        AdjFace faces[8];
+        const int n = adjacent_faces(codes, vids, w, h, x, y, v, faces);
+        // the adjacent vertices are pixels of the 3x3 neighbourhood: look their rings up through their vertex ids
+        bool hit = false;
+        for (int dy = -1; dy <= 1 && !hit; ++dy)
+            for (int dx = -1; dx <= 1 && !hit; ++dx) {
+                const int qx = x + dx, qy = y + dy;
+                if ((dx == 0 && dy == 0) || qx < 0 || qy < 0 || qx >= w || qy >= h) continue;
+                const size_t qi = (size_t)qy * w + qx;
+                if (ring_in[qi] != d - 1) continue;
+                const unsigned u = vids[qi];
+                for (int i = 0; i < n; ++i) if (faces[i].first == u || faces[i].second == u) { hit = true; break; }
+            }
+        if (hit) r = (unsigned char)d;
+    }
+    ring_out[pi] = r;
+}
+__global__ void k_conf_write(const unsigned* __restrict__ vids, const unsigned char* __restrict__ ring, size_t n, int iterations, float* __restrict__ confs)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned v = vids[i];
+    if (v == 0xFFFFFFFFu) return;
+    const int r = ring[i];
+    confs[v] = r < iterations ? (float)r / (float)iterations : 1.0f;
+}
+
 __global__ void k_fill_u32(unsigned* p, unsigned v, size_t n)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -344,15 +518,27 @@ int b200mvs_depthmap_triangulate(int device, const float* depth, int w, int h, c
                                  uint64_t cap_vertices, uint64_t cap_faces, uint64_t* n_vertices, uint64_t* n_faces,
                                  double* device_ms)
 {
-    float *d_dm = nullptr, *d_verts = nullptr, *d_colors = nullptr, *d_ctw = nullptr;
-    unsigned char *d_codes = nullptr, *d_color = nullptr;
+    return b200mvs_depthmap_pointset(device, depth, w, h, invproj, dd_factor, cam_to_world, color, color_channels, vertex_ids, vertices,
+                                     colors, faces, nullptr, nullptr, 0, nullptr, 0.f, cap_vertices, cap_faces, n_vertices, n_faces, device_ms);
+}
+
+int b200mvs_depthmap_pointset(int device, const float* depth, int w, int h, const float invproj[9], float dd_factor,
+                              const float* cam_to_world, const uint8_t* color, int color_channels,
+                              uint32_t* vertex_ids, float* vertices, float* colors, uint32_t* faces,
+                              float* normals, float* confidences, int conf_iterations, float* scales, float scale_factor,
+                              uint64_t cap_vertices, uint64_t cap_faces, uint64_t* n_vertices, uint64_t* n_faces,
+                              double* device_ms)
+{
+    float *d_dm = nullptr, *d_verts = nullptr, *d_colors = nullptr, *d_ctw = nullptr, *d_normals = nullptr, *d_confs = nullptr, *d_scales = nullptr;
+    unsigned char *d_codes = nullptr, *d_color = nullptr, *d_ring0 = nullptr, *d_ring1 = nullptr;
     unsigned long long *d_counts = nullptr, *d_offsets = nullptr;
     unsigned *d_vids = nullptr, *d_faces = nullptr;
     void* d_tmp = nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     auto cleanup = [&]() {
         for (void* p : {(void*)d_dm, (void*)d_verts, (void*)d_colors, (void*)d_ctw, (void*)d_codes, (void*)d_color, (void*)d_counts,
-                        (void*)d_offsets, (void*)d_vids, (void*)d_faces, d_tmp}) if (p) cudaFree(p);
+                        (void*)d_offsets, (void*)d_vids, (void*)d_faces, d_tmp, (void*)d_normals, (void*)d_confs, (void*)d_scales,
+                        (void*)d_ring0, (void*)d_ring1}) if (p) cudaFree(p);
         if (e0) cudaEventDestroy(e0);
         if (e1) cudaEventDestroy(e1);
     };
@@ -393,6 +579,21 @@ int b200mvs_depthmap_triangulate(int device, const float* depth, int w, int h, c
     k_fill_u32<<<(unsigned)((n + 255) / 256), 256>>>(d_vids, 0xFFFFFFFFu, n);
     k_tri_vertices<<<grd, blk>>>(d_dm, d_codes, w, h, P, d_offsets, d_ctw, d_color, color_channels, d_vids, d_verts, d_colors);
     k_tri_faces<<<grd, blk>>>(d_codes, w, h, d_offsets, d_vids, d_faces);
+    if (conf_iterations < 0) { cleanup(); return dm_fail(B200MVS_ERR_INVALID_ARG, "Invalid amount of iterations", cudaSuccess); }     // depthmap.cc:503-504
+    const bool want_conf = confidences && conf_iterations > 0;
+    if (normals) DCK(cudaMalloc(&d_normals, (nv ? nv : 1) * 12));
+    if (scales) DCK(cudaMalloc(&d_scales, (nv ? nv : 1) * 4));
+    if (want_conf) { DCK(cudaMalloc(&d_confs, (nv ? nv : 1) * 4)); DCK(cudaMalloc(&d_ring0, n)); DCK(cudaMalloc(&d_ring1, n)); }
+    if (normals || scales || want_conf)
+        k_vertex_attributes<<<grd, blk>>>(d_codes, d_vids, w, h, d_verts, scale_factor, d_normals, d_scales, d_ring0);
+    if (want_conf) {
+        unsigned char *cur = d_ring0, *nxt = d_ring1;
+        for (int d = 1; d < conf_iterations && d < 255; ++d) {
+            k_conf_ring<<<grd, blk>>>(d_codes, d_vids, w, h, cur, nxt, d);
+            unsigned char* t = cur; cur = nxt; nxt = t;
+        }
+        k_conf_write<<<(unsigned)((n + 255) / 256), 256>>>(d_vids, cur, n, conf_iterations, d_confs);
+    }
     DCK(cudaEventRecord(e1));
     DCK(cudaGetLastError());
     DCK(cudaEventSynchronize(e1));
@@ -401,6 +602,9 @@ int b200mvs_depthmap_triangulate(int device, const float* depth, int w, int h, c
     if (vertices && nv) DCK(cudaMemcpy(vertices, d_verts, nv * 12, cudaMemcpyDeviceToHost));
     if (colors && d_colors && nv) DCK(cudaMemcpy(colors, d_colors, nv * 16, cudaMemcpyDeviceToHost));
     if (faces && nf) DCK(cudaMemcpy(faces, d_faces, nf * 12, cudaMemcpyDeviceToHost));
+    if (normals && nv) DCK(cudaMemcpy(normals, d_normals, nv * 12, cudaMemcpyDeviceToHost));
+    if (scales && nv) DCK(cudaMemcpy(scales, d_scales, nv * 4, cudaMemcpyDeviceToHost));
+    if (want_conf && nv) DCK(cudaMemcpy(confidences, d_confs, nv * 4, cudaMemcpyDeviceToHost));
     cleanup();
     return 0;
 }

@@ -22,6 +22,9 @@ def _lib():
         L.b200mvs_depthmap_triangulate.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_int,
                                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p,
                                                    C.c_void_p]
+        L.b200mvs_depthmap_pointset.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_int,
+                                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                                C.c_float, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
         L._dm_ready = True
     return L
 
@@ -76,3 +79,35 @@ def depthmap_triangulate(dm: np.ndarray, invproj: np.ndarray, dd_factor: float =
                                                _p(cols), _p(faces), cap_v, cap_f, C.byref(nv), C.byref(nf), C.byref(ms)))
     return dict(vertex_ids=vids, vertices=verts[:nv.value].copy(), colors=None if cols is None else cols[:nv.value].copy(),
                 faces=faces[:nf.value].copy(), device_ms=ms.value)
+
+
+def depthmap_pointset(dm: np.ndarray, invproj: np.ndarray, dd_factor: float = DD_FACTOR_DEFAULT,
+                      cam_to_world: Optional[np.ndarray] = None, color: Optional[np.ndarray] = None,
+                      with_normals: bool = True, conf_iterations: int = 4, scale_factor: Optional[float] = 2.5, device: int = 0):
+    """The per-view work of apps/scene2pset (scene2pset.cc:264-358): triangulation + vertex normals + boundary confidences +
+    scale values. Returns the dict of depthmap_triangulate plus normals [V,3], confidences [V], scales [V] (None when skipped)."""
+    dm = np.ascontiguousarray(dm, np.float32)
+    h, w = dm.shape
+    ip = np.ascontiguousarray(invproj, np.float32).reshape(9)
+    ctw = None if cam_to_world is None else np.ascontiguousarray(cam_to_world, np.float32).reshape(16)
+    cch = 0
+    if color is not None:
+        color = np.ascontiguousarray(color, np.uint8)
+        cch = 1 if color.ndim == 2 else color.shape[2]
+    cap_v, cap_f = w * h, 2 * (w - 1) * (h - 1)
+    vids = np.empty((h, w), np.uint32)
+    verts = np.empty((cap_v, 3), np.float32)
+    cols = np.empty((cap_v, 4), np.float32) if color is not None else None
+    faces = np.empty((cap_f, 3), np.uint32)
+    nrm = np.empty((cap_v, 3), np.float32) if with_normals else None
+    cf = np.empty(cap_v, np.float32) if conf_iterations > 0 else None
+    sc = np.empty(cap_v, np.float32) if scale_factor is not None else None
+    nv, nf, ms = C.c_uint64(0), C.c_uint64(0), C.c_double(0)
+    _check(_lib().b200mvs_depthmap_pointset(device, _p(dm), w, h, _p(ip), float(dd_factor), _p(ctw), _p(color), cch, _p(vids), _p(verts),
+                                            _p(cols), _p(faces), _p(nrm), _p(cf), int(conf_iterations), _p(sc),
+                                            float(scale_factor if scale_factor is not None else 0.0), cap_v, cap_f,
+                                            C.byref(nv), C.byref(nf), C.byref(ms)))
+    n = nv.value
+    return dict(vertex_ids=vids, vertices=verts[:n].copy(), colors=None if cols is None else cols[:n].copy(), faces=faces[:nf.value].copy(),
+                normals=None if nrm is None else nrm[:n].copy(), confidences=None if cf is None else cf[:n].copy(),
+                scales=None if sc is None else sc[:n].copy(), device_ms=ms.value)

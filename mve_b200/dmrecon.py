@@ -79,7 +79,7 @@ EXPORTS = ["b200mvs_default_settings", "b200mvs_create", "b200mvs_destroy", "b20
            "b200mvs_upload_view", "b200mvs_upload_view_device", "b200mvs_set_view_camera", "b200mvs_set_features", "b200mvs_num_levels",
            "b200mvs_get_level", "b200mvs_global_view_selection", "b200mvs_optimize_patches", "b200mvs_reconstruct",
            "b200mvs_plan_views", "b200mvs_set_patch_mode", "b200mvs_depthmap_last_error", "b200mvs_depthmap_confidence_clean",
-           "b200mvs_depthmap_cleanup", "b200mvs_depthmap_triangulate"]
+           "b200mvs_depthmap_cleanup", "b200mvs_depthmap_triangulate", "b200mvs_depthmap_pointset"]
 
 
 def lib():

@@ -41,6 +41,7 @@
 #include "math/octree_tools.h"
 #include "mve/depthmap.h"
 #include "mve/mesh.h"
+#include "mve/mesh_info.h"
 #include "mve/scene.h"
 
 #include "mvs_oracle.h"
@@ -217,7 +218,8 @@ static int run_timed(int argc, char** argv)
  *   ref_harness dmops cleanup W H THRES in.f32 out.f32
  *   ref_harness dmops confclean W H in.f32 conf.f32 out.f32
  *   ref_harness dmops triangulate W H DD in.f32 COLOR.u8|- CCH  i0 .. i8  OUTPREFIX
- *       -> OUTPREFIX.vids (uint32 W*H), .verts (float32 V*3, camera coordinates), .faces (uint32 F*3), .colors (float32 V*4) */
+ *       -> OUTPREFIX.vids (uint32 W*H), .verts (float32 V*3, camera coordinates), .faces (uint32 F*3), .colors (float32 V*4),
+ *          .normals (V*3), .confs (V, depthmap_mesh_confidences(mesh, 4)), .scales (V, scene2pset's scale values x 2.5) */
 static std::vector<char> read_all(const char* path)
 {
     std::ifstream in(path, std::ios::binary);
@@ -273,6 +275,24 @@ static int run_dmops(int argc, char** argv)
         write_all(prefix + ".verts", mesh->get_vertices().data(), mesh->get_vertices().size() * 12);
         write_all(prefix + ".faces", mesh->get_faces().data(), mesh->get_faces().size() * 4);
         write_all(prefix + ".colors", mesh->get_vertex_colors().data(), mesh->get_vertex_colors().size() * 16);
+        /* the rest of the per-view work of apps/scene2pset (scene2pset.cc:316-358): normals, boundary confidences, scale */
+        mesh->ensure_normals();
+        write_all(prefix + ".normals", mesh->get_vertex_normals().data(), mesh->get_vertex_normals().size() * 12);
+        mve::geom::depthmap_mesh_confidences(mesh, 4);
+        write_all(prefix + ".confs", mesh->get_vertex_confidences().data(), mesh->get_vertex_confidences().size() * 4);
+        {
+            mve::TriangleMesh::VertexList const& mverts(mesh->get_vertices());
+            std::vector<float> mvscale(mverts.size(), 0.0f);
+            mve::MeshInfo mesh_info(mesh);
+            for (std::size_t j = 0; j < mesh_info.size(); ++j) {
+                mve::MeshInfo::VertexInfo const& vinf = mesh_info[j];
+                for (std::size_t k = 0; k < vinf.verts.size(); ++k)
+                    mvscale[j] += (mverts[j] - mverts[vinf.verts[k]]).norm();
+                mvscale[j] /= static_cast<float>(vinf.verts.size());
+                mvscale[j] *= 2.5f;
+            }
+            write_all(prefix + ".scales", mvscale.data(), mvscale.size() * 4);
+        }
         return 0;
     }
     return 2;

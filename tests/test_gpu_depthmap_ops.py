@@ -82,8 +82,18 @@ def test_triangulate_matches_reference(kind, dd, color):
         faces = np.fromfile(os.path.join(tmp, "out.faces"), np.uint32).reshape(-1, 3)
         cols = np.fromfile(os.path.join(tmp, "out.colors"), np.float32)
         cols = cols.reshape(-1, 4) if cols.size else np.zeros((0, 4), np.float32)
+        nrm = np.fromfile(os.path.join(tmp, "out.normals"), np.float32).reshape(-1, 3)
+        cfs = np.fromfile(os.path.join(tmp, "out.confs"), np.float32)
+        scl = np.fromfile(os.path.join(tmp, "out.scales"), np.float32)
     got = D.depthmap_triangulate(dm, invproj, dd_factor=dd, color=ci)
     assert len(verts) > 100 and len(faces) > 100
+    # the rest of scene2pset's per-view work: vertex normals (angle-weighted), boundary confidences (exact: ring / 4), scale values
+    ps = D.depthmap_pointset(dm, invproj, dd_factor=dd, color=ci, with_normals=True, conf_iterations=4, scale_factor=2.5)
+    assert (ps["faces"] == faces).all() and (ps["vertex_ids"] == vids).all()
+    assert (ps["confidences"] == cfs).all()
+    assert set(np.unique(cfs)).issubset({0.0, 0.25, 0.5, 0.75, 1.0}) and (cfs == 0).any() and (cfs == 1).any()
+    assert np.abs(ps["normals"] - nrm).max() <= 2e-5
+    assert np.abs(ps["scales"] - scl).max() <= 2e-6 * np.abs(scl).max()
     assert (got["vertex_ids"] == vids).all()
     assert got["faces"].shape == faces.shape and (got["faces"] == faces).all()
     assert got["vertices"].shape == verts.shape
