@@ -257,6 +257,31 @@ def test_cancel_one_view_of_a_batch():
         assert (maps[0][k] == alone[0][k]).all()
 
 
+def test_planned_views_give_the_same_maps():
+    """b200mvs_plan_views only moves the host part of DMRecon::start ahead of the call: same maps with and without a prepared
+    plan, a plan is consumed once, a plan made for other settings is ignored."""
+    import threading
+    from mve_b200 import dmrecon
+    s = golden_scene("T1")
+    g = dmrecon.Scene.from_synth(s)
+    st = dmrecon.Settings(scale=s.scale)
+    base, _ = g.reconstruct(st, [2, 5])
+    g.plan_views(st, [2, 5])
+    a, _ = g.reconstruct(st, [2, 5])
+    g.plan_views(dmrecon.Settings(scale=s.scale, global_vs_max=3), [2, 5])      # other settings: must not be used
+    b, _ = g.reconstruct(st, [2, 5])
+    # planning the next batch from another thread while a batch runs
+    th = threading.Thread(target=g.plan_views, args=(st, [2, 5]))
+    th.start()
+    c, _ = g.reconstruct(st, [4])
+    th.join()
+    d, _ = g.reconstruct(st, [2, 5])
+    for got in (a, b, d):
+        for j in range(2):
+            for k in ("depth", "conf", "dz", "view_ids"):
+                assert (got[j][k] == base[j][k]).all()
+
+
 def test_image_channel_variants():
     """Grey and RGBA inputs are expanded / stripped like image_pyramid.cc:65-73."""
     from mve_b200 import dmrecon

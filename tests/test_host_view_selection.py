@@ -60,3 +60,21 @@ def test_planning_context_refuses_compute():
     with pytest.raises(dmrecon.B200MVSError) as e:
         g.global_view_selection(st, 99)
     assert "Master view index out of bounds" in str(e.value)
+
+
+def test_plan_views_runs_on_host_threads_without_a_gpu():
+    """b200mvs_plan_views (global view selection + seed lists ahead of the reconstruct call) is pure host work: it runs in the
+    planning context, also from several threads at once; bad views are reported."""
+    import threading
+    from mve_b200 import dmrecon
+    s = golden_scene("T1")
+    g = _planning_scene(s)
+    st = dmrecon.Settings(scale=s.scale)
+    g.plan_views(st, list(range(s.n_views)))
+    th = [threading.Thread(target=g.plan_views, args=(st, [v])) for v in range(4)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    with pytest.raises(dmrecon.B200MVSError):
+        g.plan_views(st, [99])
+    with pytest.raises(dmrecon.B200MVSError):
+        g.reconstruct(st, [0])            # planning context: no compute, no CPU fallback
