@@ -138,7 +138,9 @@ typedef struct b200mvs_stats {
 #define B200MVS_DEVICE_NONE (-1)
 int  b200mvs_create(int device, int n_views, b200mvs_ctx** out);
 void b200mvs_destroy(b200mvs_ctx* ctx);
-const char* b200mvs_last_error(const b200mvs_ctx* ctx);   /* ctx may be NULL: last create() error */
+const char* b200mvs_last_error(const b200mvs_ctx* ctx);   /* ctx may be NULL: last create() error of the calling thread;
+                                                              the message of a ctx belongs to the last failing call on it (not
+                                                              synchronised: read it from the thread that got the error code) */
 const char* b200mvs_version(void);
 
 /* ---- inputs ---- */

@@ -27,7 +27,7 @@ using namespace b200mvs;
 // ------------------------------------------------------------------------------------------------
 namespace {
 
-std::string g_create_error;
+thread_local std::string g_create_error;      // last b200mvs_create error of the calling thread
 
 struct HostLevel {
     int w = 0, h = 0, pitch = 0;
@@ -1365,7 +1365,9 @@ int b200mvs_set_features(b200mvs_ctx* ctx, int n, const float* pos, const int32_
 
 int b200mvs_num_levels(b200mvs_ctx* ctx, int id)
 {
-    if (!ctx || id < 0 || id >= (int)ctx->views.size() || !ctx->views[id].valid) return B200MVS_ERR_INVALID_ARG;
+    if (!ctx) return B200MVS_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mtx);
+    if (id < 0 || id >= (int)ctx->views.size() || !ctx->views[id].valid) return B200MVS_ERR_INVALID_ARG;
     return (int)ctx->views[id].lv.size();
 }
 
@@ -1402,6 +1404,7 @@ int b200mvs_global_view_selection(b200mvs_ctx* ctx, const b200mvs_settings* s, i
     if (ref < 0 || ref >= (int)ctx->views.size()) return fail(ctx, B200MVS_ERR_INVALID_ARG, "Master view index out of bounds");
     if (!ctx->views[ref].valid) return fail(ctx, B200MVS_ERR_INVALID_ARG, "Invalid master view");
     if (s->scale >= (int)ctx->views[ref].lv.size()) return fail(ctx, B200MVS_ERR_INVALID_ARG, "Invalid scale factor");
+    if (cap > 0 && !ids_out) return fail(ctx, B200MVS_ERR_INVALID_ARG, "b200mvs_global_view_selection: ids_out is NULL");
     std::vector<int> sel = global_view_selection(ctx, *s, ref);
     for (int i = 0; i < (int)sel.size() && i < cap; ++i) ids_out[i] = sel[i];
     return (int)sel.size();
