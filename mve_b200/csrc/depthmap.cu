@@ -562,6 +562,16 @@ int b200mvs_depthmap_pointset(int device, const float* depth, int w, int h, cons
     DCK(cudaMalloc(&d_tmp, tmp_bytes));
     DCK(cudaEventCreate(&e0));
     DCK(cudaEventCreate(&e1));
+    // worst-case sized outputs, allocated before the clock starts (cudaMalloc synchronises): a vertex per pixel, two faces per block
+    const size_t max_v = n, max_f = 2 * (size_t)(w - 1) * (h - 1);
+    DCK(cudaMalloc(&d_verts, max_v * 12));
+    if (color && colors) DCK(cudaMalloc(&d_colors, max_v * 16));
+    DCK(cudaMalloc(&d_faces, (max_f ? max_f : 1) * 12));
+    if (conf_iterations < 0) { cleanup(); return dm_fail(B200MVS_ERR_INVALID_ARG, "Invalid amount of iterations", cudaSuccess); }     // depthmap.cc:503-504
+    const bool want_conf = confidences && conf_iterations > 0;
+    if (normals) DCK(cudaMalloc(&d_normals, max_v * 12));
+    if (scales) DCK(cudaMalloc(&d_scales, max_v * 4));
+    if (want_conf) { DCK(cudaMalloc(&d_confs, max_v * 4)); DCK(cudaMalloc(&d_ring0, n)); DCK(cudaMalloc(&d_ring1, n)); }
     const dim3 blk(32, 8), grd((w + 31) / 32, (h + 7) / 8);
     DCK(cudaEventRecord(e0));
     k_tri_codes<<<grd, blk>>>(d_dm, w, h, P, dd_factor, d_codes);
@@ -573,17 +583,9 @@ int b200mvs_depthmap_pointset(int device, const float* depth, int w, int h, cons
     const uint64_t nv = total >> 32, nf = total & 0xFFFFFFFFull;
     *n_vertices = nv; *n_faces = nf;
     if (nv > cap_vertices || nf > cap_faces) { cleanup(); return dm_fail(B200MVS_ERR_OVERFLOW, "depthmap_triangulate: output capacity too small", cudaSuccess); }
-    DCK(cudaMalloc(&d_verts, (nv ? nv : 1) * 12));
-    if (color && colors) DCK(cudaMalloc(&d_colors, (nv ? nv : 1) * 16));
-    DCK(cudaMalloc(&d_faces, (nf ? nf : 1) * 12));
     k_fill_u32<<<(unsigned)((n + 255) / 256), 256>>>(d_vids, 0xFFFFFFFFu, n);
     k_tri_vertices<<<grd, blk>>>(d_dm, d_codes, w, h, P, d_offsets, d_ctw, d_color, color_channels, d_vids, d_verts, d_colors);
     k_tri_faces<<<grd, blk>>>(d_codes, w, h, d_offsets, d_vids, d_faces);
-    if (conf_iterations < 0) { cleanup(); return dm_fail(B200MVS_ERR_INVALID_ARG, "Invalid amount of iterations", cudaSuccess); }     // depthmap.cc:503-504
-    const bool want_conf = confidences && conf_iterations > 0;
-    if (normals) DCK(cudaMalloc(&d_normals, (nv ? nv : 1) * 12));
-    if (scales) DCK(cudaMalloc(&d_scales, (nv ? nv : 1) * 4));
-    if (want_conf) { DCK(cudaMalloc(&d_confs, (nv ? nv : 1) * 4)); DCK(cudaMalloc(&d_ring0, n)); DCK(cudaMalloc(&d_ring1, n)); }
     if (normals || scales || want_conf)
         k_vertex_attributes<<<grd, blk>>>(d_codes, d_vids, w, h, d_verts, scale_factor, d_normals, d_scales, d_ring0);
     if (want_conf) {
