@@ -95,7 +95,7 @@ def test_triangulate_matches_reference(kind, dd, color):
     dn = np.abs(ps["normals"] - nrm).max(-1)
     assert np.percentile(dn, 99.9) <= 2e-5 and dn.max() <= 2e-3, (np.percentile(dn, 99.9), dn.max())     # acos of needle triangles
     ds = np.abs(ps["scales"] - scl) / np.abs(scl).max()
-    assert ds.max() <= 5e-6, ds.max()
+    assert ds.max() <= 3e-5, ds.max()          # float sums over <= 9 neighbours, the reference binary contracts to FMAs
     assert (got["vertex_ids"] == vids).all()
     assert got["faces"].shape == faces.shape and (got["faces"] == faces).all()
     assert got["vertices"].shape == verts.shape
