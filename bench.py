@@ -338,11 +338,17 @@ def _main(real_stdout):
     planner = concurrent.futures.ThreadPoolExecutor(max_workers=1)
     pending = [planner.submit(gscene.plan_views, settings, refs)]
 
+    plan_wait, call_host = [0.0], [0.0]
+
     def step_resident():
         flush.zero_()
+        t_w = time.perf_counter()
         pending.pop().result()
+        plan_wait[0] += time.perf_counter() - t_w
         pending.append(planner.submit(gscene.plan_views, settings, refs))
+        t_c = time.perf_counter()
         _, st = gscene.reconstruct(settings, refs, download=False)
+        call_host[0] += time.perf_counter() - t_c - 1e-3 * st.ms_total_device
         return st
 
     def step_e2e():
@@ -366,6 +372,7 @@ def _main(real_stdout):
         step_resident()
     barrier()
     stats = []
+    plan_wait[0] = call_host[0] = 0.0
     with ClockSampler(local) as clk:
         t0 = time.perf_counter()
         for _ in range(args.steps):
@@ -377,6 +384,8 @@ def _main(real_stdout):
     filled_total, _ = agg(filled_local)
     _, elapsed_max = agg(elapsed)
     _, dev_ms_max = agg(sum(s.ms_total_device for s in stats))
+    _, plan_wait_max = agg(plan_wait[0])
+    _, call_host_max = agg(call_host[0])
     value = filled_total / elapsed_max
     launches_total, _ = agg(sum(int(s.n_kernel_launches) for s in stats))
     refs_total, _ = agg(len(refs))
@@ -500,7 +509,9 @@ def _main(real_stdout):
                                  (len(needed) * W * H * 20 * 4 / 3 / 1e6),
                            "host_phase": "global view selection + seed lists of step k+1 are computed on a helper thread while the GPU runs step k (b200mvs_plan_views)",
                            "filled_px_per_step": filled_total / args.steps, "swept_px_per_step": int(refs_total) * Ws * Hs,
-                           "device_ms_per_step_max": dev_ms_max / args.steps},
+                           "device_ms_per_step_max": dev_ms_max / args.steps,
+                           "host_phase_wait_ms_per_step_max": 1e3 * plan_wait_max / args.steps,
+                           "call_minus_kernel_ms_per_step_max": 1e3 * call_host_max / args.steps},
                 "clocks": clocks, "gpu_launches": int(launches_total),
                 "e2e": {"value": f_e2e_total / e2e_max, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "steps": e2e_steps, "ms_per_step": 1e3 * e2e_max / e2e_steps},

@@ -226,25 +226,15 @@ bool in_aabb(const float* p, const b200mvs_settings& s)
 //   * `if (plx < minParallax) score *= sqr(plx / 10)` (global_view_selection.cc:80-81,93-97) needs acos only when the
 //     directions are nearly parallel: for dot < cos(minParallax + 0.05 deg) the branch is certainly not taken;
 //   * the factor of a selected view s on (candidate i, feature k) does not change between rounds; multiplying by the
-//     exact 1.0f of a not-taken branch cannot change a rounding, so only the rare factors != 1 are stored (ascending s,
-//     the std::set iteration order) and re-multiplied each round.
+//     exact 1.0f of a not-taken branch cannot change a rounding, so only the factors != 1 are stored (ascending s,
+//     the std::set iteration order) and re-multiplied each round;
+//   * the (candidate, feature) records are laid out feature-major, the order the greedy loop walks them in.
 std::vector<int> global_view_selection(const b200mvs_ctx* c, const b200mvs_settings& st, int ref)
 {
     const int nv = (int)c->views.size();
     const HostView& rv = c->views[ref];
-    std::vector<std::vector<int>> featInd(nv);
     static const std::vector<int> no_feats;
     const std::vector<int>& of_ref = ref < (int)c->view_feats.size() ? c->view_feats[ref] : no_feats;
-    for (int i : of_ref) {                       // the features with contains_view_id(refViewNr), ascending (dmrecon.cc:186-188)
-        const HostFeature& f = c->feats[i];
-        if (!point_in_frustum(rv, f.pos)) continue;
-        if (!in_aabb(f.pos, st)) continue;
-        for (int vid : f.refs) {
-            if (vid < 0 || vid >= nv || !c->views[vid].valid) continue;
-            if (point_in_frustum(c->views[vid], f.pos)) featInd[vid].push_back((int)i);
-        }
-    }
-    const size_t nf = c->feats.size();
     const float dot_skip = (float)std::cos(((double)st.min_parallax + 0.05) * 3.14159265358979323846 / 180.0);
     auto unit_dir = [&](const HostView& v, const float* p, float* d) {
         d[0] = p[0] - v.campos[0]; d[1] = p[1] - v.campos[1]; d[2] = p[2] - v.campos[2];
@@ -259,11 +249,13 @@ std::vector<int> global_view_selection(const b200mvs_ctx* c, const b200mvs_setti
         if (plx < st.min_parallax) { const float q = plx / 10.f; return q * q; }
         return 1.f;
     };
+    struct Extra { int k, view; float f; };       // a factor != 1 of selected view `view` on entry k of a candidate
     struct Cand {
-        std::vector<float> dir;          // 3 floats per entry of featInd[i]
-        std::vector<float> base;         // parallax-with-ref and resolution terms (:78-87)
-        std::vector<unsigned char> taken_ref;   // whether the ref-parallax branch multiplied (keeps `score = 1 * q*q` order)
-        std::vector<std::vector<std::pair<int, float>>> extra;   // factors != 1 of selected views, ascending view id
+        std::vector<float> base;         // per entry k (= SingleView::featInd order): parallax-with-ref and resolution terms (:78-87)
+        std::vector<int> feat;           // per entry k: local index of its feature
+        std::vector<int> ent;            // per entry k: its index in the feature-major arrays below
+        std::vector<Extra> extra;        // ascending (k, view): the std::set iteration order of :90
+        std::vector<Extra> fresh;        // the factors of the view selected last, before they are merged into `extra`
         float benefit = 0.f;             // benefitFromView of the last evaluation
         bool dirty = true;
     };
@@ -271,35 +263,42 @@ std::vector<int> global_view_selection(const b200mvs_ctx* c, const b200mvs_setti
     std::vector<char> avail(nv, 1);
     avail[ref] = 0;
     for (int v = 0; v < nv; ++v) if (!c->views[v].valid) avail[v] = 0;
-    for (int i = 0; i < nv; ++i) {
-        if (!avail[i]) continue;
-        const HostView& tv = c->views[i];
-        Cand& C = cand[i];
-        const size_t n = featInd[i].size();
-        C.dir.resize(3 * n); C.base.resize(n); C.extra.resize(n);
-        for (size_t k = 0; k < n; ++k) {
-            const float* fp = c->feats[featInd[i][k]].pos;
-            float dr[3];
-            unit_dir(rv, fp, dr);
-            unit_dir(tv, fp, &C.dir[3 * k]);
+    // Feature-major entries: everything the candidates hold about ONE feature is contiguous, because that is how the greedy
+    // loop walks it - "which candidates see a feature the new view sees" is SingleView::seesFeature (single_view.h:166-174)
+    // turned around.  A candidate's entries keep the order of the reference's featInd (ascending feature, then refs order).
+    std::vector<int> foff(1, 0), ecand, ek;
+    std::vector<float> edir;
+    for (int fi : of_ref) {                      // the features with contains_view_id(refViewNr), ascending (dmrecon.cc:186-188)
+        const HostFeature& f = c->feats[fi];
+        if (!point_in_frustum(rv, f.pos)) continue;
+        if (!in_aabb(f.pos, st)) continue;
+        const int fl = (int)foff.size() - 1;
+        bool have_ref = false;
+        float dr[3] = {0.f, 0.f, 0.f}, mfp = 0.f;
+        for (int vid : f.refs) {
+            if (vid < 0 || vid >= nv || !avail[vid]) continue;            // the reference view itself is never a candidate
+            const HostView& tv = c->views[vid];
+            if (!point_in_frustum(tv, f.pos)) continue;
+            if (!have_ref) { unit_dir(rv, f.pos, dr); mfp = foot_print(rv, st.scale, f.pos); have_ref = true; }
+            Cand& C = cand[vid];
+            const int e = (int)ecand.size();
+            float d[3];
+            unit_dir(tv, f.pos, d);
             float score = 1.f;
-            score *= plx_factor(dr, &C.dir[3 * k]);
-            const float mfp = foot_print(rv, st.scale, fp);
-            const float nfp = foot_print(tv, 0, fp);
+            score *= plx_factor(dr, d);
+            const float nfp = foot_print(tv, 0, f.pos);
             float ratio = mfp / nfp;
             if (ratio > 2.) ratio = (float)(2. / ratio);
             else if (ratio > 1.) ratio = 1.;
             score *= ratio;
-            C.base[k] = score;
+            ecand.push_back(vid); ek.push_back((int)C.base.size());
+            edir.push_back(d[0]); edir.push_back(d[1]); edir.push_back(d[2]);
+            C.base.push_back(score); C.feat.push_back(fl); C.ent.push_back(e);
         }
+        if ((int)ecand.size() > foff.back()) foff.push_back((int)ecand.size());
     }
-    // per feature: the (candidate, position in its feature list) entries that hold it - SingleView::seesFeature
-    // (single_view.h:166-174) turned around
-    std::vector<std::vector<std::pair<int, int>>> entries_of(nf);
-    for (int i = 0; i < nv; ++i)
-        if (avail[i])
-            for (size_t k = 0; k < featInd[i].size(); ++k) entries_of[featInd[i][k]].push_back(std::make_pair(i, (int)k));
     std::vector<int> selected;
+    std::vector<Extra> merged;
     bool found = true;
     while (found && selected.size() < st.global_vs_max) {
         float maxBenefit = 0.f;
@@ -312,10 +311,11 @@ std::vector<int> global_view_selection(const b200mvs_ctx* c, const b200mvs_setti
                 // recomputed only when a factor of this candidate changed since the last round: the same operations on
                 // the same operands give the same float, so caching cannot change the result
                 float benefit = 0;
-                const size_t n = featInd[i].size();
+                const size_t n = C.base.size();
+                size_t x = 0;
                 for (size_t k = 0; k < n; ++k) {
                     float score = C.base[k];
-                    for (const std::pair<int, float>& e : C.extra[k]) score *= e.second;
+                    for (; x < C.extra.size() && C.extra[x].k == (int)k; ++x) score *= C.extra[x].f;
                     benefit += score;
                 }
                 C.benefit = benefit;
@@ -327,24 +327,28 @@ std::vector<int> global_view_selection(const b200mvs_ctx* c, const b200mvs_setti
         selected.insert(std::upper_bound(selected.begin(), selected.end(), maxView), maxView);
         avail[maxView] = 0;
         // fold the new view's factors into every remaining candidate.  Only (candidate, feature) entries whose feature
-        // the new view sees can change (global_view_selection.cc:90-92), so walk the new view's features and, through the
-        // per-feature list of entries, the candidates that hold each of them.
-        const int sv = maxView;
-        for (size_t ks = 0; ks < featInd[sv].size(); ++ks) {
-            const int fid = featInd[sv][ks];
-            if (ks > 0 && featInd[sv][ks - 1] == fid) continue;        // seesFeature() is a predicate: a duplicate adds nothing
-            const float* ds = &cand[sv].dir[3 * ks];
-            for (const std::pair<int, int>& ik : entries_of[fid]) {
-                const int i = ik.first, k = ik.second;
+        // the new view sees can change (global_view_selection.cc:90-92).
+        const Cand& S = cand[maxView];
+        for (size_t ks = 0; ks < S.base.size(); ++ks) {
+            const int fl = S.feat[ks];
+            if (ks > 0 && S.feat[ks - 1] == fl) continue;              // seesFeature() is a predicate: a duplicate adds nothing
+            const float* ds = &edir[3 * (size_t)S.ent[ks]];
+            for (int e = foff[fl]; e < foff[fl + 1]; ++e) {
+                const int i = ecand[e];
                 if (!avail[i]) continue;
-                Cand& C = cand[i];
-                const float f = plx_factor(ds, &C.dir[3 * k]);
-                if (f != 1.f) {
-                    std::vector<std::pair<int, float>>& ex = C.extra[k];
-                    ex.insert(std::upper_bound(ex.begin(), ex.end(), std::make_pair(sv, -1e30f)), std::make_pair(sv, f));
-                    C.dirty = true;
-                }
+                const float f = plx_factor(ds, &edir[3 * (size_t)e]);
+                if (f != 1.f) cand[i].fresh.push_back(Extra{ek[e], maxView, f});      // arrives with ascending k
             }
+        }
+        for (int i = 0; i < nv; ++i) {
+            Cand& C = cand[i];
+            if (C.fresh.empty()) continue;
+            merged.resize(C.extra.size() + C.fresh.size());
+            std::merge(C.extra.begin(), C.extra.end(), C.fresh.begin(), C.fresh.end(), merged.begin(),
+                       [](const Extra& a, const Extra& b) { return a.k != b.k ? a.k < b.k : a.view < b.view; });
+            C.extra.swap(merged);
+            C.fresh.clear();
+            C.dirty = true;
         }
     }
     return selected;
@@ -359,12 +363,11 @@ std::vector<Seed> collect_seeds(const b200mvs_ctx* c, const b200mvs_settings& st
     const HostView& rv = c->views[ref];
     std::vector<Seed> out;
     // "use feature if visible in reference view or at least one neighboring view" (dmrecon.cc:260-276), in feature order
-    std::vector<int> ids;
-    if (ref < (int)c->view_feats.size()) ids = c->view_feats[ref];
-    for (int g : gsel) if (g >= 0 && g < (int)c->view_feats.size()) ids.insert(ids.end(), c->view_feats[g].begin(), c->view_feats[g].end());
-    std::sort(ids.begin(), ids.end());
-    ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
-    for (int fi : ids) {
+    std::vector<char> wanted(c->feats.size(), 0);
+    if (ref < (int)c->view_feats.size()) for (int fi : c->view_feats[ref]) wanted[fi] = 1;
+    for (int g : gsel) if (g >= 0 && g < (int)c->view_feats.size()) for (int fi : c->view_feats[g]) wanted[fi] = 1;
+    for (size_t fi = 0; fi < wanted.size(); ++fi) {
+        if (!wanted[fi]) continue;
         const HostFeature& f = c->feats[fi];
         if (!point_in_frustum(rv, f.pos)) continue;
         if (!in_aabb(f.pos, st)) continue;
@@ -1042,45 +1045,51 @@ int upload_common(b200mvs_ctx* ctx, int id, const uint8_t* d_src, int w, int h, 
                   const float* pp, const float* rot, const float* trans, cudaStream_t stream)
 {
     HostView& v = ctx->views[id];
+    bool same_camera = false;
     {
         // prepared plans depend on cameras and image sizes only: a re-upload of the same view with the same camera keeps them
-        const bool same = v.valid && v.w == w && v.h == h && v.flen == flen && v.paspect == paspect && v.pp[0] == pp[0] && v.pp[1] == pp[1] &&
-                          std::memcmp(v.rot, rot, sizeof(v.rot)) == 0 && std::memcmp(v.trans, trans, sizeof(v.trans)) == 0;
-        if (!same) { std::lock_guard<std::mutex> pl(ctx->plan_mtx); ctx->plans.clear(); }
+        same_camera = v.valid && !v.lv.empty() && v.w == w && v.h == h && v.flen == flen && v.paspect == paspect && v.pp[0] == pp[0] && v.pp[1] == pp[1] &&
+                      std::memcmp(v.rot, rot, sizeof(v.rot)) == 0 && std::memcmp(v.trans, trans, sizeof(v.trans)) == 0;
+        if (!same_camera) { std::lock_guard<std::mutex> pl(ctx->plan_mtx); ctx->plans.clear(); }
     }
-    v.valid = false;
-    v.has_image = false;
-    v.w = w; v.h = h; v.flen = flen; v.paspect = paspect; v.pp[0] = pp[0]; v.pp[1] = pp[1];
-    std::memcpy(v.rot, rot, sizeof(v.rot));
-    std::memcpy(v.trans, trans, sizeof(v.trans));
-    // CameraInfo::fill_camera_pos / fill_world_to_cam (camera.cc:34-39,61-67)
-    v.campos[0] = -rot[0] * trans[0] - rot[3] * trans[1] - rot[6] * trans[2];
-    v.campos[1] = -rot[1] * trans[0] - rot[4] * trans[1] - rot[7] * trans[2];
-    v.campos[2] = -rot[2] * trans[0] - rot[5] * trans[1] - rot[8] * trans[2];
-    for (int r = 0; r < 3; ++r) {
-        v.w2c[4 * r] = rot[3 * r]; v.w2c[4 * r + 1] = rot[3 * r + 1]; v.w2c[4 * r + 2] = rot[3 * r + 2]; v.w2c[4 * r + 3] = trans[r];
-    }
-    // buildPyramid (image_pyramid.cc:22-53)
-    v.lv.clear();
-    float ppx = pp[0], ppy = pp[1];
-    int cw = w, chh = h;
-    auto push_level = [&]() {
-        HostLevel L; L.w = cw; L.h = chh; L.pitch = (cw + 3) & ~3;
-        fill_calibration(v, ppx, ppy, (float)cw, (float)chh, L.proj, L.invproj);
-        v.lv.push_back(L);
-    };
-    push_level();
-    while (std::min(cw, chh) >= 30) {
-        if (cw % 2 == 1) ppx = ppx * float(cw) / float(cw + 1);
-        if (chh % 2 == 1) ppy = ppy * float(chh) / float(chh + 1);
-        cw = (cw + 1) / 2; chh = (chh + 1) / 2;
+    // An unchanged camera keeps its host-side record untouched: b200mvs_plan_views of other views may be reading it right
+    // now (cameras, calibrations and level sizes; never the device pointers written below).
+    if (!same_camera) {
+        v.valid = false;
+        v.has_image = false;
+        v.w = w; v.h = h; v.flen = flen; v.paspect = paspect; v.pp[0] = pp[0]; v.pp[1] = pp[1];
+        std::memcpy(v.rot, rot, sizeof(v.rot));
+        std::memcpy(v.trans, trans, sizeof(v.trans));
+        // CameraInfo::fill_camera_pos / fill_world_to_cam (camera.cc:34-39,61-67)
+        v.campos[0] = -rot[0] * trans[0] - rot[3] * trans[1] - rot[6] * trans[2];
+        v.campos[1] = -rot[1] * trans[0] - rot[4] * trans[1] - rot[7] * trans[2];
+        v.campos[2] = -rot[2] * trans[0] - rot[5] * trans[1] - rot[8] * trans[2];
+        for (int r = 0; r < 3; ++r) {
+            v.w2c[4 * r] = rot[3 * r]; v.w2c[4 * r + 1] = rot[3 * r + 1]; v.w2c[4 * r + 2] = rot[3 * r + 2]; v.w2c[4 * r + 3] = trans[r];
+        }
+        // buildPyramid (image_pyramid.cc:22-53)
+        v.lv.clear();
+        float ppx = pp[0], ppy = pp[1];
+        int cw = w, chh = h;
+        auto push_level = [&]() {
+            HostLevel L; L.w = cw; L.h = chh; L.pitch = (cw + 3) & ~3;
+            fill_calibration(v, ppx, ppy, (float)cw, (float)chh, L.proj, L.invproj);
+            v.lv.push_back(L);
+        };
         push_level();
+        while (std::min(cw, chh) >= 30) {
+            if (cw % 2 == 1) ppx = ppx * float(cw) / float(cw + 1);
+            if (chh % 2 == 1) ppy = ppy * float(chh) / float(chh + 1);
+            cw = (cw + 1) / 2; chh = (chh + 1) / 2;
+            push_level();
+        }
     }
     if ((int)v.lv.size() > MAX_LEVELS) return fail(ctx, B200MVS_ERR_UNSUPPORTED, "image too large: %d pyramid levels", (int)v.lv.size());
     if (!d_src) {
         // camera only (SingleView::create, single_view.cc:24-53): the image follows with an upload if the view turns out
         // to be a reference view or a selected neighbour (loadColorImage, dmrecon.cc:78,238-240)
         if (v.d_base) { cudaFree(v.d_base); v.d_base = nullptr; v.bytes = 0; }
+        v.has_image = false;
         v.valid = true;
         ctx->views_dirty = true;
         return 0;
@@ -1405,7 +1414,15 @@ int b200mvs_global_view_selection(b200mvs_ctx* ctx, const b200mvs_settings* s, i
     if (!ctx->views[ref].valid) return fail(ctx, B200MVS_ERR_INVALID_ARG, "Invalid master view");
     if (s->scale >= (int)ctx->views[ref].lv.size()) return fail(ctx, B200MVS_ERR_INVALID_ARG, "Invalid scale factor");
     if (cap > 0 && !ids_out) return fail(ctx, B200MVS_ERR_INVALID_ARG, "b200mvs_global_view_selection: ids_out is NULL");
-    std::vector<int> sel = global_view_selection(ctx, *s, ref);
+    std::vector<int> sel;
+    bool planned = false;
+    {
+        // a plan prepared by b200mvs_plan_views already holds the selection (it stays there for b200mvs_reconstruct)
+        std::lock_guard<std::mutex> pl(ctx->plan_mtx);
+        auto it = ctx->plans.find(ref);
+        if (it != ctx->plans.end() && std::memcmp(&it->second.settings, s, sizeof(*s)) == 0) { sel = it->second.gsel; planned = true; }
+    }
+    if (!planned) sel = global_view_selection(ctx, *s, ref);
     for (int i = 0; i < (int)sel.size() && i < cap; ++i) ids_out[i] = sel[i];
     return (int)sel.size();
 }
@@ -1574,31 +1591,36 @@ int b200mvs_reconstruct(b200mvs_ctx* ctx, const b200mvs_settings* s, int n_refs,
     // apps/dmrecon/dmrecon.cc:285): spread it over host threads.
     std::vector<std::vector<Seed>> seed_lists(n_refs);
     {
-        std::atomic<int> next_job(0);
+        // a plan prepared ahead (b200mvs_plan_views, possibly while the previous batch was running) is used once
+        std::vector<int> todo;
+        {
+            std::lock_guard<std::mutex> pl(ctx->plan_mtx);
+            for (int j = 0; j < n_refs; ++j) {
+                if (progress) { progress[j].status = 1; progress[j].start_time = (uint64_t)t_start; progress[j].filled = 0; progress[j].queue_size = 0; }
+                auto it = ctx->plans.find(refs[j]);
+                if (it != ctx->plans.end() && std::memcmp(&it->second.settings, s, sizeof(*s)) == 0) {
+                    gsels[j] = std::move(it->second.gsel);
+                    seed_lists[j] = std::move(it->second.seeds);
+                    ctx->plans.erase(it);
+                    if (progress) progress[j].status = 2;
+                } else {
+                    todo.push_back(j);
+                }
+            }
+        }
+        std::atomic<size_t> next_job(0);
         auto worker = [&]() {
             for (;;) {
-                const int j = next_job.fetch_add(1);
-                if (j >= n_refs) break;
-                if (progress) { progress[j].status = 1; progress[j].start_time = (uint64_t)t_start; progress[j].filled = 0; progress[j].queue_size = 0; }
-                {
-                    // a plan prepared ahead (b200mvs_plan_views, possibly while the previous batch was running) is used once
-                    std::lock_guard<std::mutex> pl(ctx->plan_mtx);
-                    auto it = ctx->plans.find(refs[j]);
-                    if (it != ctx->plans.end() && std::memcmp(&it->second.settings, s, sizeof(*s)) == 0) {
-                        gsels[j] = std::move(it->second.gsel);
-                        seed_lists[j] = std::move(it->second.seeds);
-                        ctx->plans.erase(it);
-                        if (progress) progress[j].status = 2;
-                        continue;
-                    }
-                }
+                const size_t k = next_job.fetch_add(1);
+                if (k >= todo.size()) break;
+                const int j = todo[k];
                 gsels[j] = global_view_selection(ctx, *s, refs[j]);
                 if (gsels[j].empty()) continue;
                 if (progress) progress[j].status = 2;
                 seed_lists[j] = collect_seeds(ctx, *s, refs[j], gsels[j]);
             }
         };
-        const int n_threads = std::max(1, std::min<int>(n_refs, (int)std::thread::hardware_concurrency()));
+        const int n_threads = std::max(1, std::min<int>((int)todo.size(), (int)std::thread::hardware_concurrency()));
         std::vector<std::thread> pool;
         for (int t = 1; t < n_threads; ++t) pool.emplace_back(worker);
         worker();

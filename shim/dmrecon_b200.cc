@@ -74,6 +74,7 @@ struct DeviceCtx {
     bool features_set = false;
     bool cameras_set = false;
     bool leader_active = false;
+    int planners = 0;               // callers that run their global view selection right now and will enqueue next
     std::vector<Request*> pending;
     uint64_t arrivals = 0;          // bumped by every enqueue: the leader's collection window watches it
     size_t last_batch = 0;          // size of the previous batch = how many callers to expect
@@ -258,7 +259,7 @@ DMRecon::start()
 
     /* (Re)create the device context for this scene; cameras and features are registered once per context. */
     if (D.ctx == nullptr || D.scene != scene || D.embedding != settings.imageEmbedding) {
-        while (D.leader_active) D.cv.wait(lock);
+        while (D.leader_active || D.planners > 0) D.cv.wait(lock);
         if (D.ctx) { b200mvs_destroy(D.ctx); D.ctx = nullptr; }
         int rc = b200mvs_create(D.device, (int)mve_views.size(), &D.ctx);
         if (rc != 0) throw std::runtime_error(b200mvs_last_error(nullptr));
@@ -275,7 +276,7 @@ DMRecon::start()
        neighbours (loadColorImage, dmrecon.cc:78,238-240), once per view and context. */
     progress.status = RECON_FEATURES;
     if (!D.cameras_set) {
-        while (D.leader_active) D.cv.wait(lock);
+        while (D.leader_active || D.planners > 0) D.cv.wait(lock);
         for (std::size_t i = 0; i < mve_views.size(); ++i) {
             mve::View::Ptr v = mve_views[i];
             if (v == nullptr || !v->is_camera_valid() || !v->has_image(settings.imageEmbedding, mve::IMAGE_TYPE_UINT8))
@@ -297,7 +298,7 @@ DMRecon::start()
             for (std::size_t j = 0; j < features[i].refs.size(); ++j) ids.push_back(features[i].refs[j].view_id);
             off[i + 1] = (int32_t)ids.size();
         }
-        while (D.leader_active) D.cv.wait(lock);
+        while (D.leader_active || D.planners > 0) D.cv.wait(lock);
         int rc = b200mvs_set_features(ctx, (int)features.size(), pos.data(), off.data(), ids.data());
         if (rc != 0) throw_for(rc, b200mvs_last_error(ctx));
         D.features_set = true;
@@ -337,6 +338,18 @@ DMRecon::start()
     req.maps.conf = confImg->get_data_pointer();
     std::memset(&req.stats, 0, sizeof(req.stats));
 
+    /* Global view selection + seed list (dmrecon.cc:96-98,211-292) on the CALLER's thread, like the reference, where every
+       DMRecon of the OpenMP team does its own: in parallel over the team and while the GPU still runs the previous batch.
+       The result is parked in the context (b200mvs_plan_views); the leader's b200mvs_global_view_selection and
+       b200mvs_reconstruct pick it up instead of computing it again. */
+    progress.status = RECON_GLOBALVS;
+    D.planners++;
+    lock.unlock();
+    b200mvs_plan_views(ctx, &s, 1, &req.ref);        // a failure shows up again, with its message, in the leader's call
+    lock.lock();
+    D.planners--;
+    if (progress.cancelled) { D.cv.notify_all(); progress.status = RECON_CANCELLED; return; }
+
     /* Submit.  Whoever finds no leader becomes one and runs batches until the queue is empty. */
     D.pending.push_back(&req);
     D.arrivals++;
@@ -345,16 +358,18 @@ DMRecon::start()
         D.leader_active = true;
         while (!D.pending.empty()) {
             /* Collection window: the other threads of the caller's OpenMP team reach this point within microseconds to
-               milliseconds of each other (they all finished the previous batch together).  Wait until as many requests
-               as the previous batch had are here, or nothing new has arrived for 3 ms, at most 30 ms. */
+               milliseconds of each other (they all finished the previous batch together).  Callers that are computing
+               their view selection right now (D.planners) are certain to arrive: wait for them (at most 250 ms).  Beyond
+               that: until as many requests as the previous batch had are here, or nothing new has arrived for 3 ms, at
+               most 30 ms. */
             const auto t_open = std::chrono::steady_clock::now();
             uint64_t seen = D.arrivals;
             for (;;) {
-                if (D.last_batch > 1 && D.pending.size() >= D.last_batch) break;
+                if (D.planners == 0 && D.last_batch > 1 && D.pending.size() >= D.last_batch) break;
                 const bool woke = D.cv.wait_for(lock, std::chrono::milliseconds(3), [&]() { return D.arrivals != seen; });
-                if (!woke) break;
+                if (!woke && D.planners == 0) break;
                 seen = D.arrivals;
-                if (std::chrono::steady_clock::now() - t_open > std::chrono::milliseconds(30)) break;
+                if (std::chrono::steady_clock::now() - t_open > std::chrono::milliseconds(D.planners > 0 ? 250 : 30)) break;
             }
             std::vector<Request*> batch;
             std::vector<Request*> rest;
