@@ -435,7 +435,7 @@ def _main(real_stdout):
     except Exception:
         pass
     roofline = {"kernel": "k_frontier (persistent cooperative kernel: seeds + every frontier round of the step in one launch; "
-                          "8 lanes per patch)", "bound": "hbm",
+                          "one PatchOptimization per thread in large rounds, per warp in small ones)", "bound": "hbm",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                 "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_filled_px": bpp,

@@ -91,7 +91,8 @@ def test_triangulate_matches_reference(kind, dd, color):
     ps = D.depthmap_pointset(dm, invproj, dd_factor=dd, color=ci, with_normals=True, conf_iterations=4, scale_factor=2.5)
     assert (ps["faces"] == faces).all() and (ps["vertex_ids"] == vids).all()
     assert (ps["confidences"] == cfs).all()
-    assert set(np.unique(cfs)).issubset({0.0, 0.25, 0.5, 0.75, 1.0}) and (cfs == 0).any() and (cfs == 1).any()
+    assert set(np.unique(cfs)).issubset({0.0, 0.25, 0.5, 0.75, 1.0}) and (cfs == 0).any()
+    assert kind == "ragged" or (cfs == 1).any()        # a ragged map may have no vertex further than 4 rings from a boundary
     dn = np.abs(ps["normals"] - nrm).max(-1)
     assert np.percentile(dn, 99.9) <= 2e-5 and dn.max() <= 2e-3, (np.percentile(dn, 99.9), dn.max())     # acos of needle triangles
     ds = np.abs(ps["scales"] - scl) / np.abs(scl).max()
