@@ -199,9 +199,9 @@ struct PatchT {
             const uint4* Lquad = nullptr;
             bool dok = false;
             {
-                const float4 wa = __ldg(reinterpret_cast<const float4*>(&V->w2c[0]));
-                const float4 wb = __ldg(reinterpret_cast<const float4*>(&V->w2c[4]));
-                const float4 wc = __ldg(reinterpret_cast<const float4*>(&V->w2c[8]));
+                const float4 wa = ldg_keep(reinterpret_cast<const float4*>(&V->w2c[0]));
+                const float4 wb = ldg_keep(reinterpret_cast<const float4*>(&V->w2c[4]));
+                const float4 wc = ldg_keep(reinterpret_cast<const float4*>(&V->w2c[8]));
                 A0x = wa.x * c0x + wa.y * c0y + wa.z * c0z + wa.w;
                 A0y = wb.x * c0x + wb.y * c0y + wb.z * c0z + wb.w;
                 A0z = wc.x * c0x + wc.y * c0y + wc.z * c0z + wc.w;
@@ -218,8 +218,8 @@ struct PatchT {
                     while (ratio < 0.5f) { ++l; ratio *= 2.f; }
                     const int nl = __ldg(&V->nlevels);
                     if (l > nl - 1) l = nl - 1;                     // clampLevel, minLevel = 0 (single_view.h:113-123)
-                    const float4 kk = __ldg(reinterpret_cast<const float4*>(&V->lv[l].ax));
-                    const int4 g = __ldg(reinterpret_cast<const int4*>(&V->lv[l].w));
+                    const float4 kk = ldg_keep(reinterpret_cast<const float4*>(&V->lv[l].ax));
+                    const int4 g = ldg_keep(reinterpret_cast<const int4*>(&V->lv[l].w));
                     Lax = kk.x; Lay = kk.y; Lcx = kk.z; Lcy = kk.w; wm1 = (float)(g.x - 1); hm1 = (float)(g.y - 1); Lpitch = g.z;
                     Lquad = reinterpret_cast<const uint4*>(__ldg(reinterpret_cast<const unsigned long long*>(&V->lv[l].quad)));
                     // projections of patchPoints[12] and patchPoints[12] + masterViewDirs[12]
@@ -251,10 +251,15 @@ struct PatchT {
                 const bool gn_direct = !candidates && (r & 2u) && (second || !cs_view);
                 const bool gn_sums = !candidates && (r & 2u) && !second && cs_view && !want_normal;
                 float S1a = 0.f, S1b = 0.f, S1c = 0.f, S2a = 0.f, S2b = 0.f, S2c = 0.f, Sen = 0.f;
-                float Mna = 0.f, Mnb = 0.f, Mnc = 0.f, Nna = 0.f, Nnb = 0.f, Nnc = 0.f;
-                float Dma = 0.f, Dmb = 0.f, Dmc = 0.f, Dna = 0.f, Dnb = 0.f, Dnc = 0.f, Dda = 0.f, Ddb = 0.f, Ddc = 0.f;
-                float vnum = 0.f, vden = 0.f;
-                float A0 = 0.f, A1 = 0.f, A2 = 0.f, A3 = 0.f, A4 = 0.f, A5 = 0.f, B0 = 0.f, B1 = 0.f, B2 = 0.f;
+                // A sweep either updates the colour scale (sums Mn, Nn and, when a depth step follows, Dm, Dn, Dd) or forms the
+                // Gauss-Newton products directly (vnum, vden, A, B) - never both (do_cs excludes gn_direct), so the two groups
+                // share their registers: 15 accumulators instead of 26 in the hottest loop of the kernel.
+                float X0 = 0.f, X1 = 0.f, X2 = 0.f, X3 = 0.f, X4 = 0.f, X5 = 0.f, X6 = 0.f, X7 = 0.f, X8 = 0.f, X9 = 0.f, X10 = 0.f,
+                      X11 = 0.f, X12 = 0.f, X13 = 0.f, X14 = 0.f;
+                float &Mna = X0, &Mnb = X1, &Mnc = X2, &Nna = X3, &Nnb = X4, &Nnc = X5;
+                float &Dma = X6, &Dmb = X7, &Dmc = X8, &Dna = X9, &Dnb = X10, &Dnc = X11, &Dda = X12, &Ddb = X13, &Ddc = X14;
+                float &vnum = X0, &vden = X1;
+                float &A0 = X2, &A1 = X3, &A2 = X4, &A3 = X5, &A4 = X6, &A5 = X7, &B0 = X8, &B1 = X9, &B2 = X10;
                 bool oob = false;
                 // The sample loop is software-pipelined: the geometry of sample k+1 is evaluated and its two loads (quad texel
                 // of the neighbour, master texel) are issued BEFORE sample k is processed, so their latency is covered by the
@@ -290,7 +295,7 @@ struct PatchT {
                         } \
                         const int left_ = (int)floorf(qx_), top_ = (int)floorf(qy_); \
                         nfx = qx_ - (float)left_; nfy = qy_ - (float)top_; \
-                        nQ = __ldg(Lquad + (size_t)top_ * Lpitch + left_); \
+                        nQ = ldg_texel(Lquad + (size_t)top_ * Lpitch + left_); \
                         nmt = *reinterpret_cast<const unsigned*>(mptr); \
                     } \
                 } while (0)
@@ -389,8 +394,9 @@ struct PatchT {
                     for (int i = 0; i < MAX_LOCAL; ++i) if (i == k) { cs[i][0] = c0; cs[i][1] = c1; cs[i][2] = c2; }
                 }
                 if (gn_sums) {
-                    vnum = c0 * (Dma - c0 * Dna) + c1 * (Dmb - c1 * Dnb) + c2 * (Dmc - c2 * Dnc);
-                    vden = c0 * c0 * Dda + c1 * c1 * Ddb + c2 * c2 * Ddc;
+                    const float vn = c0 * (Dma - c0 * Dna) + c1 * (Dmb - c1 * Dnb) + c2 * (Dmc - c2 * Dnc);
+                    const float vd = c0 * c0 * Dda + c1 * c1 * Ddb + c2 * c2 * Ddc;
+                    vnum = vn; vden = vd;                  // (Mn, Nn, whose registers these are, have been consumed above)
                 }
                 if (gn_direct || gn_sums) {
                     num += vnum; den += vden;
