@@ -473,10 +473,19 @@ __global__ void k_export_rgb(const uchar4* __restrict__ src, int w, int h, int p
 #define OPT_MIN_BLOCKS 1     // CTAs per SM: registers per thread <= 65536 / (OPT_MIN_BLOCKS * OPT_TPB) = 128; shared memory 32 KB per CTA
 #endif
 constexpr int OPT_WARPS = OPT_TPB / 32;
-// dynamic shared memory of the kernels that optimise patches: the lane-replicated sRGB table
-constexpr size_t OPT_SMEM_BYTES = sizeof(float) * (256 * LUT_REP);
 using PatchT = b200mvs::PatchW;    // one warp per patch (latency: small rounds)
 using PatchT1 = b200mvs::PatchT;   // one thread per patch (throughput: large rounds)
+// dynamic shared memory of the kernels that optimise patches: the lane-replicated sRGB table, then one PatchT1 per thread.
+// The state of a thread's patch is live across the whole sample loop, which needs every register there is: left to the
+// compiler it is spilled to local memory (~100 slots x 128 B per warp - more than L1 holds, so every reload in the per-view
+// set-up and tear-down was an L2 round trip: 19 % of the kernel's time in ncu's stall samples).  In shared memory a reload
+// costs a fixed ~30 cycles.
+constexpr size_t OPT_LUT_BYTES = sizeof(float) * (256 * LUT_REP);
+constexpr size_t OPT_SMEM_BYTES = OPT_LUT_BYTES + (size_t)OPT_TPB * sizeof(PatchT1);
+__device__ __forceinline__ PatchT1& thread_patch(float* smem)
+{
+    return reinterpret_cast<PatchT1*>(reinterpret_cast<unsigned char*>(smem) + OPT_LUT_BYTES)[threadIdx.x];
+}
 
 __device__ __forceinline__ Entry load_entry(const Entry* p)       // lists are rewritten by other SMs every round: bypass L1
 {
@@ -585,7 +594,7 @@ k_optimize(const Entry* __restrict__ in, PatchOut* __restrict__ out, int n, int 
     for (int i = threadIdx.x; i < 256 * LUT_REP; i += blockDim.x) smem[i] = g_lut[i / LUT_REP];
     __syncthreads();
     if (mode == 2 || (mode == 0 && n >= OPT_THREAD_MIN)) {
-        PatchT1 p;
+        PatchT1& p = thread_patch(smem);
         bind_thread(p, st, views, smem, (int)threadIdx.x);
         optimise_entries_t(p, in, out, (unsigned long long)n, &counters[C_TICKET], jobs, counters);
     } else {
@@ -909,7 +918,7 @@ k_frontier(const FrontierParams P)
         const bool by_thread = n_thread > 0ull;
         // the PatchOptimizations of the round
         if (by_thread) {
-            PatchT1 pt;
+            PatchT1& pt = thread_patch(smem);
             bind_thread(pt, P.st, P.views, smem, (int)threadIdx.x);
             optimise_entries_t(pt, run_cur, P.res, n_thread, &ctl->ticket, P.jobs, cnt, &ctl->thread_busy_ns);
             __syncwarp();

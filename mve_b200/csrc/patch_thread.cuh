@@ -37,8 +37,7 @@ struct PatchT {
     unsigned lane4;            // 4 * (lane of this thread)
     // ---- constants of the patch ----
     const JobParams* job;
-    const ViewParams* rv;
-    int x0, y0;
+    unsigned xy;               // x | y << 16 of the patch centre
     float u0x, u0y, u0z;       // R^T K^-1 (x + .5, y + .5, 1): un-normalised ray of the centre pixel
     float uax, uay, uaz;       // R^T K^-1 (1, 0, 0): change of the ray per pixel in x
     float ubx, uby, ubz;       // R^T K^-1 (0, 1, 0): ... in y
@@ -49,28 +48,41 @@ struct PatchT {
     float mfp, inv_mfp;        // footPrintScaled(patchPoints[12]) and its reciprocal
     float mm, inv_mm, sqrDevX; // masterMeanCol, its reciprocal, sqrDevX
     float depth, dzI, dzJ;
-    bool ref_ok;               // sampler->success[refViewNr]
-    int nsel;
     unsigned avail;            // LocalViewSelection::available over global slots
     int iter;
-    bool opti, converged, lvs_ok;
     unsigned n_sets;
-    int stage;
-    bool viewRemoved, was_normal, normal;
+    // Everything small lives in ONE register (`pk`): the state of a patch stays live across the whole sample loop, and
+    // every register it occupies there is a register the loop spills (profiles/r2_notes.md, "state packing").
+    //   bits 0-9   flags F_*          bits 10-12 stage        bits 13-15 nsel (size of the selected set)
+    //   bits 16-19 p_col_ok           bits 20-23 p_der_ok     (per selected view: colour / derivative samples valid in the last pass)
+    //   bits 24-27 |NCC - oldNCC| > minRefineDiff per selected view, taken when the last pass overwrote the NCC (the
+    //              reference keeps a copy, oldNCC, for this one comparison: patch_optimization.cc:196-199,217-225)
+    unsigned pk;
+    unsigned selp;             // the selected set: 4 x uint8 global slots, ascending, 0xFF = none
     // ---- per selected view (index = position in the ascending selected set) ----
-    int sel[MAX_LOCAL];        // global slot, 0xFF = none
     float cs[MAX_LOCAL][3];    // colorScale
     float ncc[MAX_LOCAL];      // NCC at the state of the last pass
-    float oldn[MAX_LOCAL];     // oldNCC
-    float cand[MAX_GLOBAL];    // NCC of candidate global slots (local view selection; rare path, may live in local memory)
     // ---- results of the last pass ----
-    unsigned p_col_ok, p_der_ok;
     float p_num, p_den;
     float nX0, nX1, nX2;
-    bool n_singular;
-    bool p_has_normal, p_has_ncc;
+
 
     enum Stage { LVS_CTOR, CTOR, FIRST, PRE, POST, LVS_REPL, REPL, DONE };
+    enum : unsigned {
+        F_REF_OK = 1u << 0,        // sampler->success[refViewNr]
+        F_OPTI = 1u << 1, F_CONVERGED = 1u << 2, F_LVS_OK = 1u << 3, F_VIEW_REMOVED = 1u << 4, F_WAS_NORMAL = 1u << 5,
+        F_NORMAL = 1u << 6, F_SINGULAR = 1u << 7, F_HAS_NORMAL = 1u << 8, F_HAS_NCC = 1u << 9
+    };
+    static constexpr int SH_STAGE = 10, SH_NSEL = 13, SH_COL = 16, SH_DER = 20, SH_DF = 24;
+    __device__ __forceinline__ bool is(unsigned f) const { return (pk & f) != 0u; }
+    __device__ __forceinline__ void put(unsigned f, bool v) { pk = v ? (pk | f) : (pk & ~f); }
+    __device__ __forceinline__ int stage() const { return (int)((pk >> SH_STAGE) & 7u); }
+    __device__ __forceinline__ void set_stage(int v) { pk = (pk & ~(7u << SH_STAGE)) | ((unsigned)v << SH_STAGE); }
+    __device__ __forceinline__ int nsel() const { return (int)((pk >> SH_NSEL) & 7u); }
+    __device__ __forceinline__ void set_nsel(int v) { pk = (pk & ~(7u << SH_NSEL)) | ((unsigned)v << SH_NSEL); }
+    __device__ __forceinline__ int sel(int k) const { return (int)((selp >> (8 * k)) & 0xFFu); }
+    __device__ __forceinline__ int px() const { return (int)(xy & 0xFFFFu); }
+    __device__ __forceinline__ int py() const { return (int)(xy >> 16); }
 
     // ---- register arrays with a dynamic index ----
     template <typename T> static __device__ __forceinline__ T get4(const T (&a)[MAX_LOCAL], int k)
@@ -81,6 +93,19 @@ struct PatchT {
     {
 #pragma unroll
         for (int i = 0; i < MAX_LOCAL; ++i) if (i == k) a[i] = v;
+    }
+
+    // The table is the first thing in the kernels' dynamic shared memory (b200mvs.cu, OPT_SMEM_BYTES).  Read through the
+    // member - the object itself lives in shared memory - the compiler would no longer know which address space it points
+    // to and emit generic loads for the 15 look-ups of every sample.
+    __device__ __forceinline__ const float* table() const
+    {
+#if defined(B200MVS_HOST_EMU)
+        return lut_tab;
+#else
+        extern __shared__ float b200mvs_dyn_smem[];
+        return b200mvs_dyn_smem;
+#endif
     }
 
     // un-normalised ray of the sample with pixel offsets (di, dj), its reciprocal length and the sample's depth parameter
@@ -101,10 +126,11 @@ struct PatchT {
             const float t = depth + (float)(k % 5 - 2) * dzI + (float)(k / 5 - 2) * dzJ;
             bad |= t <= 0.f;
         }
-        if (bad) ref_ok = false;
+        if (bad) pk &= ~F_REF_OK;
         cpx = c0x + depth * crx;
         cpy = c0y + depth * cry;
         cpz = c0z + depth * crz;
+        const ViewParams* rv = &views[job->ref_view];
         const float z = __ldg(&rv->w2c[8]) * cpx + __ldg(&rv->w2c[9]) * cpy + __ldg(&rv->w2c[10]) * cpz + __ldg(&rv->w2c[11]);
         mfp = z * job->ki0;     // single_view.h:160-164
         inv_mfp = rcp_fast(mfp);
@@ -113,12 +139,15 @@ struct PatchT {
     // PatchSampler ctor (patch_sampler.cc:19-62) + computeMasterSamples (:298-345)
     __device__ __forceinline__ void init_sampler(int x, int y)
     {
-        ref_ok = false; mm = 0.f; inv_mm = 0.f; sqrDevX = 0.f;
+        const float* const lut_tab = table();
+        const unsigned lane4 = this->lane4;
+        pk &= ~F_REF_OK; mm = 0.f; inv_mm = 0.f; sqrDevX = 0.f;
         mx0 = mx1 = mx2 = 0.f;
         crx = cry = crz = cpx = cpy = cpz = mfp = inv_mfp = 0.f;
         if (x - 2 < 0 || y - 2 < 0 || x + 2 > job->W - 1 || y + 2 > job->H - 1) return;
         {
             // viewRayScaled (single_view.cc:99-106, depthmap.cc:149-156): K^-1 has the sparsity of camera.cc:180-200
+            const ViewParams* rv = &views[job->ref_view];
             const float r0 = __ldg(&rv->rot[0]), r1 = __ldg(&rv->rot[1]), r2 = __ldg(&rv->rot[2]), r3 = __ldg(&rv->rot[3]), r4 = __ldg(&rv->rot[4]);
             const float r5 = __ldg(&rv->rot[5]), r6 = __ldg(&rv->rot[6]), r7 = __ldg(&rv->rot[7]), r8 = __ldg(&rv->rot[8]);
             const float vx = job->ki0 * ((float)x + 0.5f) + job->ki2, vy = job->ki4 * ((float)y + 0.5f) + job->ki5;
@@ -129,7 +158,7 @@ struct PatchT {
             const float inv = rsqrt_fast(u0x * u0x + u0y * u0y + u0z * u0z);
             crx = u0x * inv; cry = u0y * inv; crz = u0z * inv;
         }
-        ref_ok = true;
+        pk |= F_REF_OK;
         // master colours: mean, then the per-channel means and deviations of the normalised colours
         const uchar4* row = job->ref_img + (size_t)(y - 2) * job->ref_pitch + (x - 2);
         float s0 = 0.f, s1 = 0.f, s2 = 0.f;
@@ -143,7 +172,7 @@ struct PatchT {
             row += job->ref_pitch;
         }
         mm = (s0 + s1 + s2) / (3.f * NS);
-        if (mm < 0.01f || mm > 0.99f) { ref_ok = false; return; }
+        if (mm < 0.01f || mm > 0.99f) { pk &= ~F_REF_OK; return; }
         inv_mm = 1.f / mm;
         mx0 = (s0 * inv_mm) / (float)NS; mx1 = (s1 * inv_mm) / (float)NS; mx2 = (s2 * inv_mm) / (float)NS;
         row = job->ref_img + (size_t)(y - 2) * job->ref_pitch + (x - 2);
@@ -165,24 +194,35 @@ struct PatchT {
     // PatchSampler::update (patch_sampler.cc:259-271)
     __device__ __forceinline__ void update()
     {
-        ref_ok = true;
+        pk |= F_REF_OK;
         compute_points();
     }
 
     // One pass at the current state (same contract as PatchW::pass).
-    __device__ __forceinline__ void pass(bool candidates, bool cs_pending, bool want_ncc, bool want_normal)
+    // `cand`: NCC per candidate global slot, written by a candidates pass for the lvs_greedy() that follows it.
+    __device__ __forceinline__ void pass(bool candidates, bool cs_pending, bool want_ncc, bool want_normal, float* cand)
     {
+        // The object lives in shared memory (k_frontier): what the sample loop reads 25 times per sweep is copied into
+        // registers here, everything else is read where it is needed.
+        const float* const lut_tab = table();
+        const unsigned lane4 = this->lane4;
+        const float u0x = this->u0x, u0y = this->u0y, u0z = this->u0z, uax = this->uax, uay = this->uay, uaz = this->uaz;
+        const float ubx = this->ubx, uby = this->uby, ubz = this->ubz;
+        const float depth = this->depth, dzI = this->dzI, dzJ = this->dzJ;
+        const float mx0 = this->mx0, mx1 = this->mx1, mx2 = this->mx2, mm = this->mm, inv_mm = this->inv_mm;
+        const JobParams* const job = this->job;
         float num = 0.f, den = 0.f;
         double D0 = 0.0, D1 = 0.0, D2 = 0.0, D3 = 0.0, D4 = 0.0, D5 = 0.0, E0 = 0.0, E1 = 0.0, E2 = 0.0;
         bool cs_active = cs_pending && st->use_color_scale;
-        if (!candidates) { p_col_ok = p_der_ok = 0u; }
-        const int count = candidates ? job->n_global : nsel;
+        if (!candidates) pk &= want_ncc ? ~((0xFFu << SH_COL) | (0xFu << SH_DF)) : ~(0xFFu << SH_COL);     // p_col_ok = p_der_ok = 0
+        const int count = candidates ? job->n_global : nsel();
+        const int x0 = px(), y0 = py();
         const float pv0 = mx0 * mm, pv1 = mx1 * mm, pv2 = mx2 * mm;      // pivots of the NCC sums
 #pragma unroll 1
         for (int k = 0; k < count; ++k) {
             int slot = k;
             if (candidates) { if (!((avail >> k) & 1u)) continue; }
-            else slot = get4(sel, k);
+            else slot = sel(k);
             const ViewParams* V = &views[job->gview[slot]];
             ++n_sets;
             float c0 = 1.f, c1 = 1.f, c2 = 1.f;
@@ -274,8 +314,8 @@ struct PatchT {
                 bool nvalid = false;
                 // geometry + loads of the sample at (ndi, ndj)
 #define B200MVS_STAGE_NEXT() do { \
-                    float ux_, uy_, uz_, inv_; \
-                    sample_ray(ndi, ndj, ux_, uy_, uz_, inv_); \
+                    const float ux_ = u0x + ndi * uax + ndj * ubx, uy_ = u0y + ndi * uay + ndj * uby, uz_ = u0z + ndi * uaz + ndj * ubz; \
+                    const float inv_ = rsqrt_fast(ux_ * ux_ + uy_ * uy_ + uz_ * uz_); \
                     const float t_ = depth + ndi * dzI + ndj * dzJ; \
                     const float s1_ = t_ * inv_; \
                     const float wx_ = W0x + ndi * Wax + ndj * Wbx, wy_ = W0y + ndi * Way + ndj * Wby, wz_ = W0z + ndi * Waz + ndj * Wbz; \
@@ -385,9 +425,9 @@ struct PatchT {
                     for (int ch = 0; ch < 3; ++ch) {
                         if ((double)fabsf(aa[ch]) > 1e-6) {
                             cc[ch] += ab[ch] * rcp_fast(aa[ch]);
-                            if ((double)cc[ch] > 1e3) opti = false;
+                            if ((double)cc[ch] > 1e3) pk &= ~F_OPTI;
                         } else
-                            opti = false;
+                            pk &= ~F_OPTI;
                     }
                     c0 = cc[0]; c1 = cc[1]; c2 = cc[2];
 #pragma unroll
@@ -409,11 +449,15 @@ struct PatchT {
                 }
             }
             if (!candidates) {
-                if (r & 1u) p_col_ok |= 1u << k;
-                if (r & 2u) p_der_ok |= 1u << k;
+                if (r & 1u) pk |= 1u << (SH_COL + k);
+                if (r & 2u) pk |= 1u << (SH_DER + k);
                 // computeColorScale: a failed view ends the whole update (`return`, not `continue`, patch_optimization.cc:92-93)
                 if (cs_active && !(r & 1u)) cs_active = false;
-                if (want_ncc) set4(ncc, k, (r & 1u) ? nccv : -1.f);
+                if (want_ncc) {
+                    const float v = (r & 1u) ? nccv : -1.f;
+                    if (fabsf(v - get4(ncc, k)) > st->min_refine_diff) pk |= 1u << (SH_DF + k);
+                    set4(ncc, k, v);
+                }
             } else {
                 const float v = (r & 1u) ? nccv : -1.f;
                 if (v < st->min_ncc) avail &= ~(1u << k);
@@ -422,14 +466,14 @@ struct PatchT {
         }
         if (candidates) return;
         p_num = num; p_den = den;
-        p_has_normal = want_normal;
-        p_has_ncc = want_ncc;
+        put(F_HAS_NORMAL, want_normal);
+        put(F_HAS_NCC, want_ncc);
         if (want_normal) {
             // matrix_tools.h:392-398,460-475
             const double m[9] = {D0, D1, D2, D1, D3, D4, D2, D4, D5};
             const double det = m[0] * m[4] * m[8] + m[1] * m[5] * m[6] + m[2] * m[3] * m[7]
                              - m[2] * m[4] * m[6] - m[1] * m[3] * m[8] - m[0] * m[5] * m[7];
-            n_singular = det == 0.0;
+            put(F_SINGULAR, det == 0.0);
             double inv[9];
             inv[0] = m[4] * m[8] - m[5] * m[7];
             inv[1] = m[2] * m[7] - m[1] * m[8];
@@ -448,16 +492,16 @@ struct PatchT {
         }
     }
 
-    __device__ __forceinline__ bool all_der_ok() const { return p_der_ok == ((1u << nsel) - 1u); }
+    __device__ __forceinline__ bool all_der_ok() const { return ((pk >> SH_DER) & 0xFu) == ((1u << nsel()) - 1u); }
 
     // optimizeDepthOnly (patch_optimization.cc:265-299) from the sums of the last pass. Returns true when the state moved.
     __device__ __forceinline__ bool depth_step()
     {
-        if (!all_der_ok()) { opti = false; return false; }
+        if (!all_der_ok()) { pk &= ~F_OPTI; return false; }
         if (p_den > 0.f) {
             depth += p_num / p_den;
             update();
-            opti = ref_ok;
+            put(F_OPTI, is(F_REF_OK));
             return true;
         }
         return false;
@@ -466,44 +510,51 @@ struct PatchT {
     // optimizeDepthAndNormal (patch_optimization.cc:302-364) from the solution prepared by the last pass.
     __device__ __forceinline__ bool normal_step()
     {
-        if (!all_der_ok()) { opti = false; return false; }
-        if (n_singular) { opti = false; return false; }
+        if (!all_der_ok()) { pk &= ~F_OPTI; return false; }
+        if (is(F_SINGULAR)) { pk &= ~F_OPTI; return false; }
         dzI += nX1; dzJ += nX2; depth += nX0;
         update();
-        opti = ref_ok;
+        put(F_OPTI, is(F_REF_OK));
         return true;
     }
 
     // ---- sorted insert / erase on the selected set (std::set semantics) ----
     __device__ __forceinline__ void sel_erase_mask(unsigned mask)       // bit k: remove element k
     {
+        const int n = nsel();
         int cnt = 0;
+        unsigned packed = 0xFFFFFFFFu;
 #pragma unroll
         for (int k = 0; k < MAX_LOCAL; ++k) {
-            if (k < nsel && !((mask >> k) & 1u)) {
+            if (k < n && !((mask >> k) & 1u)) {
                 // element k moves to position cnt (cnt <= k)
-                const int s = sel[k];
+                const unsigned s8 = (selp >> (8 * k)) & 0xFFu;
                 const float a = cs[k][0], b = cs[k][1], c = cs[k][2], v = ncc[k];
+                packed = (packed & ~(0xFFu << (8 * cnt))) | (s8 << (8 * cnt));
 #pragma unroll
-                for (int q = 0; q < MAX_LOCAL; ++q) if (q == cnt) { sel[q] = s; cs[q][0] = a; cs[q][1] = b; cs[q][2] = c; ncc[q] = v; }
+                for (int q = 0; q < MAX_LOCAL; ++q) if (q == cnt) { cs[q][0] = a; cs[q][1] = b; cs[q][2] = c; ncc[q] = v; }
                 ++cnt;
             }
         }
-#pragma unroll
-        for (int q = 0; q < MAX_LOCAL; ++q) if (q >= cnt) sel[q] = 0xFF;
-        nsel = cnt;
+        selp = packed;
+        set_nsel(cnt);
     }
     __device__ __forceinline__ void sel_insert(int slot, float cs_init)
     {
+        const int n = nsel();
         int pos = 0;
 #pragma unroll
-        for (int k = 0; k < MAX_LOCAL; ++k) if (k < nsel && sel[k] < slot) ++pos;
+        for (int k = 0; k < MAX_LOCAL; ++k) if (k < n && sel(k) < slot) ++pos;
 #pragma unroll
         for (int q = MAX_LOCAL - 1; q > 0; --q)
-            if (q > pos && q <= nsel) { sel[q] = sel[q - 1]; cs[q][0] = cs[q - 1][0]; cs[q][1] = cs[q - 1][1]; cs[q][2] = cs[q - 1][2]; ncc[q] = ncc[q - 1]; }
+            if (q > pos && q <= n) { cs[q][0] = cs[q - 1][0]; cs[q][1] = cs[q - 1][1]; cs[q][2] = cs[q - 1][2]; ncc[q] = ncc[q - 1]; }
 #pragma unroll
-        for (int q = 0; q < MAX_LOCAL; ++q) if (q == pos) { sel[q] = slot; cs[q][0] = cs[q][1] = cs[q][2] = cs_init; ncc[q] = 0.f; }
-        ++nsel;
+        for (int q = 0; q < MAX_LOCAL; ++q) if (q == pos) { cs[q][0] = cs[q][1] = cs[q][2] = cs_init; ncc[q] = 0.f; }
+        // bytes below `pos` stay, the byte at `pos` becomes the new slot, the bytes above move up by one
+        const unsigned low = pos == 0 ? 0u : (selp & (0xFFFFFFFFu >> (32 - 8 * pos)));
+        const unsigned high = pos >= 3 ? 0u : ((selp >> (8 * pos)) << (8 * (pos + 1)));
+        selp = low | ((unsigned)slot << (8 * pos)) | high;
+        set_nsel(n + 1);
     }
 
     // viewDir / epipolar plane / footprint of global slot `slot` at patchPoints[12] (local_view_selection.cc:93-131)
@@ -522,7 +573,7 @@ struct PatchT {
     }
 
     // Second half of LocalViewSelection::performVS (local_view_selection.cc:86-147)
-    __device__ __forceinline__ void lvs_greedy()
+    __device__ __forceinline__ void lvs_greedy(const float* cand)
     {
         const unsigned N = st->nr_recon_neighbors;
         const float cs_init = 1.f / mm;
@@ -533,7 +584,7 @@ struct PatchT {
         }
         const int G = job->n_global;
         bool found = true;
-        while ((unsigned)nsel < N && found) {
+        while ((unsigned)nsel() < N && found) {
             found = false;
             float maxScore = 0.f;
             int maxView = 0;
@@ -546,10 +597,11 @@ struct PatchT {
                 if (mfp / nfp < 0.5f) score *= 0.01f;
                 float dp = clamp1(rdx * vdx + rdy * vdy + rdz * vdz);
                 score *= plx_weight(deg_acos(dp));
+                const int ns = nsel();
 #pragma unroll 1
-                for (int k = 0; k < nsel; ++k) {
+                for (int k = 0; k < ns; ++k) {
                     float sx, sy, sz, ex, ey, ez, sfp;
-                    cand_geometry(get4(sel, k), rdx, rdy, rdz, sx, sy, sz, ex, ey, ez, sfp);
+                    cand_geometry(sel(k), rdx, rdy, rdz, sx, sy, sz, ex, ey, ez, sfp);
                     dp = clamp1(sx * vdx + sy * vdy + sz * vdz);
                     score *= plx_weight(deg_acos(dp));
                     dp = clamp1(epx * ex + epy * ey + epz * ez);
@@ -565,102 +617,102 @@ struct PatchT {
                 avail &= ~(1u << maxView);
             }
         }
-        if ((unsigned)nsel == N) lvs_ok = true;
+        if ((unsigned)nsel() == N) pk |= F_LVS_OK;
     }
 
     // PatchOptimization ctor (patch_optimization.cc:21-78) incl. LocalViewSelection ctor (local_view_selection.cc:19-54)
     __device__ __forceinline__ void begin(const JobParams* j, const PatchIn& in)
     {
         job = j;
-        rv = &views[job->ref_view];
-        x0 = in.x; y0 = in.y;
+        xy = ((unsigned)in.x & 0xFFFFu) | ((unsigned)in.y << 16);
         depth = in.depth; dzI = in.dzI; dzJ = in.dzJ;
-        iter = 0; opti = true; converged = false; lvs_ok = false;
-        nsel = 0; avail = 0u;
-        p_col_ok = p_der_ok = 0u; p_num = p_den = 0.f; p_has_normal = p_has_ncc = false;
-        nX0 = nX1 = nX2 = 0.f; n_singular = true;
-        viewRemoved = was_normal = normal = false;
-        stage = DONE;
+        iter = 0;
+        pk = F_OPTI | F_SINGULAR | ((unsigned)DONE << SH_STAGE);      // opti = true, n_singular = true, everything else clear
+        avail = 0u;
+        p_num = p_den = 0.f;
+        nX0 = nX1 = nX2 = 0.f;
         u0x = u0y = u0z = uax = uay = uaz = ubx = uby = ubz = c0x = c0y = c0z = 0.f;
         init_sampler(in.x, in.y);
+        selp = in.slots;                                 // propagated ids arrive ascending, 0xFF padded
+        int n = 0;
 #pragma unroll
         for (int k = 0; k < MAX_LOCAL; ++k) {
-            sel[k] = (in.slots >> (8 * k)) & 0xFF;       // propagated ids arrive ascending, 0xFF padded
-            if (sel[k] != 0xFF) nsel = k + 1;
-            cs[k][0] = cs[k][1] = cs[k][2] = 0.f; ncc[k] = 0.f; oldn[k] = 0.f;
+            if (sel(k) != 0xFF) n = k + 1;
+            cs[k][0] = cs[k][1] = cs[k][2] = 0.f; ncc[k] = 0.f;
         }
-        if (!ref_ok) { opti = false; return; }
+        set_nsel(n);
+        if (!is(F_REF_OK)) { pk &= ~F_OPTI; return; }
         const unsigned N = st->nr_recon_neighbors;
-        if ((unsigned)nsel == N) lvs_ok = true;
-        else if ((unsigned)nsel > N) {
-            nsel = 0;
-#pragma unroll
-            for (int k = 0; k < MAX_LOCAL; ++k) sel[k] = 0xFF;
+        if ((unsigned)n == N) pk |= F_LVS_OK;
+        else if ((unsigned)n > N) {
+            n = 0;
+            set_nsel(0);
+            selp = 0xFFFFFFFFu;
         }
         avail = job->n_global >= 32 ? FULL : ((1u << job->n_global) - 1u);
 #pragma unroll
-        for (int k = 0; k < MAX_LOCAL; ++k) if (k < nsel) avail &= ~(1u << sel[k]);
+        for (int k = 0; k < MAX_LOCAL; ++k) if (k < n) avail &= ~(1u << sel(k));
         const float ci = 1.f / mm;
 #pragma unroll
         for (int k = 0; k < MAX_LOCAL; ++k) { cs[k][0] = cs[k][1] = cs[k][2] = ci; }
-        stage = lvs_ok ? CTOR : LVS_CTOR;
+        set_stage(is(F_LVS_OK) ? CTOR : LVS_CTOR);
     }
 
     // doAutoOptimization as a state machine around the single pass() call site (see PatchW::step)
     __device__ __forceinline__ bool step()
     {
+        int stage = this->stage();
         if (stage == DONE) return true;
         const bool a_cand = (stage == LVS_CTOR) | (stage == LVS_REPL);
-        const bool a_cs = (stage == CTOR) | (stage == REPL) | ((stage == POST) & was_normal);
+        const bool a_cs = (stage == CTOR) | (stage == REPL) | ((stage == POST) & is(F_WAS_NORMAL));
         const bool a_ncc = (stage == PRE) | (stage == POST) | (stage == REPL) | ((stage == FIRST) & (iter == 4));
-        const bool a_normal = (stage == REPL) | ((stage == FIRST) & (iter == 4)) | ((stage == PRE) & normal) |
+        const bool a_normal = (stage == REPL) | ((stage == FIRST) & (iter == 4)) | ((stage == PRE) & is(F_NORMAL)) |
                               ((stage == POST) & ((iter + 1) % 5 == 4));
-        pass(a_cand, a_cs, a_ncc, a_normal);
+        float cand[MAX_GLOBAL];      // candidates' NCCs: local memory, touched on the (rare) view-selection passes only
+        pass(a_cand, a_cs, a_ncc, a_normal, cand);
         if (stage == LVS_CTOR || stage == LVS_REPL) {
-            lvs_greedy();
-            if (!lvs_ok) { if (stage == LVS_CTOR) opti = false; stage = DONE; return true; }
-            stage = (stage == LVS_CTOR) ? CTOR : REPL;
+            lvs_greedy(cand);
+            if (!is(F_LVS_OK)) { if (stage == LVS_CTOR) pk &= ~F_OPTI; set_stage(DONE); return true; }
+            set_stage((stage == LVS_CTOR) ? CTOR : REPL);
             return false;
         }
-        if (!opti) { stage = DONE; return true; }
+        if (!is(F_OPTI)) { set_stage(DONE); return true; }
         if (stage == POST) {
-            bool conv = true;
-            unsigned tbr = 0u;
+            // `abs(ncc - oldNCC) > minRefineDiff` per view was taken when the pass overwrote the NCC (pass(), want_ncc)
+            const int n = nsel();
+            const unsigned dfb = (pk >> SH_DF) & ((1u << n) - 1u);
+            unsigned tbr = (iter == 14) ? dfb : 0u;
 #pragma unroll
-            for (int k = 0; k < MAX_LOCAL; ++k) {
-                if (k >= nsel) continue;
-                const float df = fabsf(ncc[k] - oldn[k]);
-                if (df > st->min_refine_diff) conv = false;
-                if (ncc[k] < st->accept_ncc || (iter == 14 && df > st->min_refine_diff)) tbr |= 1u << k;
-            }
+            for (int k = 0; k < MAX_LOCAL; ++k)
+                if (k < n && ncc[k] < st->accept_ncc) tbr |= 1u << k;
             if (tbr) {
-                viewRemoved = true;
+                pk |= F_VIEW_REMOVED;
                 sel_erase_mask(tbr);          // LocalViewSelection::replaceViews (local_view_selection.cc:150-160)
-                lvs_ok = false;
-                stage = LVS_REPL;
+                pk &= ~F_LVS_OK;
+                set_stage(LVS_REPL);
                 return false;
             }
-            if (conv) { converged = true; stage = DONE; return true; }
+            if (dfb == 0u) { pk |= F_CONVERGED; set_stage(DONE); return true; }
             ++iter;
         } else if (stage == REPL) {
             ++iter;
         }
-        while (iter < 4 && opti) {
+        while (iter < 4 && is(F_OPTI)) {
             const bool moved = depth_step();
             ++iter;
-            if (moved && opti) { stage = FIRST; return false; }
+            if (moved && is(F_OPTI)) { set_stage(FIRST); return false; }
         }
-        if (!opti) { stage = DONE; return true; }
-        if (!((unsigned)iter < st->max_iterations && lvs_ok)) { stage = DONE; return true; }
-        normal = (iter % 5 == 4) || viewRemoved;
-        if (!p_has_ncc || (normal && !p_has_normal)) { stage = PRE; return false; }
-#pragma unroll
-        for (int k = 0; k < MAX_LOCAL; ++k) oldn[k] = ncc[k];
-        opti = false;
-        if (normal) { normal_step(); viewRemoved = false; was_normal = true; }
-        else { depth_step(); was_normal = false; }
-        if (!opti) { stage = DONE; return true; }
-        stage = POST;
+        if (!is(F_OPTI)) { set_stage(DONE); return true; }
+        if (!((unsigned)iter < st->max_iterations && is(F_LVS_OK))) { set_stage(DONE); return true; }
+        const bool normal = (iter % 5 == 4) || is(F_VIEW_REMOVED);
+        put(F_NORMAL, normal);
+        if (!is(F_HAS_NCC) || (normal && !is(F_HAS_NORMAL))) { set_stage(PRE); return false; }
+        // (oldNCC = ncc here in the reference: the comparison is taken when the next pass overwrites the NCC)
+        pk &= ~F_OPTI;
+        if (normal) { normal_step(); pk &= ~F_VIEW_REMOVED; pk |= F_WAS_NORMAL; }
+        else { depth_step(); pk &= ~F_WAS_NORMAL; }
+        if (!is(F_OPTI)) { set_stage(DONE); return true; }
+        set_stage(POST);
         return false;
     }
 
@@ -669,17 +721,15 @@ struct PatchT {
     {
         out.depth = depth; out.dzI = dzI; out.dzJ = dzJ;
         out.iterations = iter;
-        out.flags = (converged ? 1 : 0) | (opti ? 2 : 0);
-        unsigned s = 0u;
-#pragma unroll
-        for (int k = 0; k < MAX_LOCAL; ++k) s |= (unsigned)((k < nsel) ? (sel[k] & 0xFF) : 0xFF) << (8 * k);
-        out.slots = s;
+        out.flags = (is(F_CONVERGED) ? 1 : 0) | (is(F_OPTI) ? 2 : 0);
+        const int n = nsel();
+        out.slots = n >= 4 ? selp : (selp | (0xFFFFFFFFu << (8 * n)));
         out.conf = 0.f; out.nx = out.ny = out.nz = 0.f;
-        if (!converged) return;
+        if (!is(F_CONVERGED)) return;
         float mean = 0.f;
 #pragma unroll
-        for (int k = 0; k < MAX_LOCAL; ++k) if (k < nsel) mean += ncc[k];
-        mean /= (float)nsel;
+        for (int k = 0; k < MAX_LOCAL; ++k) if (k < n) mean += ncc[k];
+        mean /= (float)n;
         const float score = (mean - st->accept_ncc) / (1.f - st->accept_ncc);
         // patchPoints[14] - patchPoints[10] and patchPoints[2] - patchPoints[22]
         float px[4], py[4], pz[4];
@@ -702,11 +752,18 @@ struct PatchT {
     }
 };
 
+#if !defined(B200MVS_HOST_EMU)
+// PatchT objects sit side by side in shared memory (k_frontier).  With 8-byte members the stride cannot be an odd number of
+// words; 2 mod 4 words keeps the conflicts of a warp's accesses to one member at 2-way (these are the once-per-sweep
+// accesses, not the table look-ups of the sample loop).
+static_assert(sizeof(PatchT) % 16 == 8, "PatchT stride in shared memory must be 8 mod 16 bytes");
+#endif
+
 __device__ __forceinline__ void bind_thread(PatchT& p, const DevSettings* st, const ViewParams* views, const float* lut_rep, int tid)
 {
     p.st = st; p.views = views;
     p.lut_tab = lut_rep; p.lane4 = 4u * (unsigned)(tid & (LUT_REP - 1));
-    p.stage = PatchT::DONE;
+    p.pk = (unsigned)PatchT::DONE << PatchT::SH_STAGE;
     p.n_sets = 0u;
 }
 
