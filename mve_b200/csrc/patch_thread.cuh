@@ -335,10 +335,12 @@ struct PatchT {
                         } \
                         const int left_ = (int)floorf(qx_), top_ = (int)floorf(qy_); \
                         nfx = qx_ - (float)left_; nfy = qy_ - (float)top_; \
-                        nQ = ldg_texel(Lquad + (size_t)top_ * Lpitch + left_); \
+                        noff = (unsigned)top_ * (unsigned)Lpitch + (unsigned)left_; \
+                        nQ = ldg_texel(Lquad + noff); \
                         nmt = *reinterpret_cast<const unsigned*>(mptr); \
                     } \
                 } while (0)
+                unsigned noff = 0u;
                 B200MVS_STAGE_NEXT();
 #ifdef B200MVS_T1_UNROLL2
 #pragma unroll 2
