@@ -273,6 +273,9 @@ def _main(real_stdout):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        # one process per GPU on one box: the host phase (b200mvs_plan_views) of every rank starts at the same moment, so
+        # each rank takes its share of the cores and leaves the launching threads alone (read by the library per call)
+        os.environ.setdefault("B200MVS_HOST_THREADS", str(max(2, (os.cpu_count() or 16) // (2 * world))))
 
     cfg = workload_cfg(args.workload, world)
     owned = sharding.owned_views(cfg["views"], rank, world)      # views this rank renders / uploads (every view has one owner)

@@ -356,6 +356,15 @@ std::vector<int> global_view_selection(const b200mvs_ctx* c, const b200mvs_setti
 
 using Seed = SeedPoint;
 
+// Host threads for the per-view host phase (global view selection + seed lists).  One process per GPU on a shared box
+// should not start hardware_concurrency() threads each: B200MVS_HOST_THREADS caps it (bench.py sets cores / (2 * ranks)).
+int host_threads(int n_jobs)
+{
+    int cap = (int)std::thread::hardware_concurrency();
+    if (const char* e = std::getenv("B200MVS_HOST_THREADS")) { const int v = std::atoi(e); if (v > 0) cap = v; }
+    return std::max(1, std::min(n_jobs, cap));
+}
+
 // The feature loop of DMRecon::processFeatures (dmrecon.cc:258-292): which features seed, at which pixel, with
 // which initial depth.  The optimisation of the seeds runs on the device.
 std::vector<Seed> collect_seeds(const b200mvs_ctx* c, const b200mvs_settings& st, int ref, const std::vector<int>& gsel)
@@ -1466,7 +1475,7 @@ int b200mvs_plan_views(b200mvs_ctx* ctx, const b200mvs_settings* s, int n_refs, 
             if (!made[j].gsel.empty()) made[j].seeds = collect_seeds(ctx, *s, r, made[j].gsel);
         }
     };
-    const int n_threads = std::max(1, std::min<int>(n_refs, (int)std::thread::hardware_concurrency()));
+    const int n_threads = host_threads(n_refs);
     std::vector<std::thread> pool;
     for (int t = 1; t < n_threads; ++t) pool.emplace_back(worker);
     worker();
@@ -1629,7 +1638,7 @@ int b200mvs_reconstruct(b200mvs_ctx* ctx, const b200mvs_settings* s, int n_refs,
                 seed_lists[j] = collect_seeds(ctx, *s, refs[j], gsels[j]);
             }
         };
-        const int n_threads = std::max(1, std::min<int>((int)todo.size(), (int)std::thread::hardware_concurrency()));
+        const int n_threads = host_threads((int)todo.size());
         std::vector<std::thread> pool;
         for (int t = 1; t < n_threads; ++t) pool.emplace_back(worker);
         worker();
