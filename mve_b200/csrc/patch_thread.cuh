@@ -313,11 +313,6 @@ struct PatchT {
                 unsigned nmt = 0u;
                 bool nvalid = false;
                 // geometry + loads of the sample at (ndi, ndj)
-#if defined(B200MVS_MASTER_LDG) && !defined(B200MVS_HOST_EMU)
-#define B200MVS_MASTER_LOAD(p) __ldg(p)
-#else
-#define B200MVS_MASTER_LOAD(p) (*(p))
-#endif
 #define B200MVS_STAGE_NEXT() do { \
                     const float ux_ = u0x + ndi * uax + ndj * ubx, uy_ = u0y + ndi * uay + ndj * uby, uz_ = u0z + ndi * uaz + ndj * ubz; \
                     const float inv_ = rsqrt_fast(ux_ * ux_ + uy_ * uy_ + uz_ * uz_); \
@@ -342,7 +337,7 @@ struct PatchT {
                         nfx = qx_ - (float)left_; nfy = qy_ - (float)top_; \
                         noff = (unsigned)top_ * (unsigned)Lpitch + (unsigned)left_; \
                         nQ = ldg_texel(Lquad + noff); \
-                        nmt = B200MVS_MASTER_LOAD(reinterpret_cast<const unsigned*>(mptr)); \
+                        nmt = *reinterpret_cast<const unsigned*>(mptr); \
                     } \
                 } while (0)
                 unsigned noff = 0u;

@@ -74,4 +74,8 @@ def map_parity(ref, got):
                dz_abs_p99=float(np.percentile(np.abs(ref["dz"] - got["dz"])[both].max(-1), 99)), n_both=int(both.sum()))
     if "view_ids" in ref and "view_ids" in got:
         res["view_ids_equal"] = float((ref["view_ids"] == got["view_ids"]).all(-1)[both].mean())
+        a, b = ref["view_ids"][both], got["view_ids"][both]
+        shared = ((a[:, :, None] == b[:, None, :]) & (a[:, :, None] >= 0)).any(-1).sum(-1)
+        res["view_ids_shared_mean"] = float(shared.mean())          # of the (up to) 4 local views of a pixel
+        res["view_ids_share_ge3"] = float((shared >= 3).mean())
     return res
