@@ -17,13 +17,6 @@
 #include <stdint.h>
 #include <cstddef>
 
-#ifndef B200MVS_TEXEL_POLICY
-#define B200MVS_TEXEL_POLICY 0
-#endif
-#ifndef B200MVS_PARAM_POLICY
-#define B200MVS_PARAM_POLICY 0
-#endif
-
 namespace b200mvs {
 
 constexpr int MAX_LEVELS = 12;
@@ -89,41 +82,6 @@ __device__ __forceinline__ float rsqrt_fast(float x) { return 1.f / sqrtf(x); }
 #else
 __device__ __forceinline__ float rcp_fast(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float rsqrt_fast(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
-#endif
-
-// Loads with an L1 eviction priority.  The sampled texels stream through L1 (~1 MB per SM and frontier round) while the
-// small tables every sweep starts from (ViewParams, JobParams) and the spilled per-patch state want to stay: texels are
-// loaded evict-first, tables evict-last (profiles/r2_notes.md, "L1 priorities").
-#if defined(B200MVS_HOST_EMU)
-__device__ __forceinline__ uint4 ldg_texel(const uint4* p) { return *p; }
-template <typename T> __device__ __forceinline__ T ldg_keep(const T* p) { return *p; }
-#else
-__device__ __forceinline__ uint4 ldg_texel(const uint4* p)
-{
-#if B200MVS_TEXEL_POLICY == 1
-    uint4 v; asm("ld.global.nc.L1::evict_first.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p)); return v;
-#elif B200MVS_TEXEL_POLICY == 2
-    uint4 v; asm("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p)); return v;
-#else
-    return __ldg(p);
-#endif
-}
-__device__ __forceinline__ float4 ldg_keep(const float4* p)
-{
-#if B200MVS_PARAM_POLICY == 1
-    float4 v; asm("ld.global.nc.L1::evict_last.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p)); return v;
-#else
-    return __ldg(p);
-#endif
-}
-__device__ __forceinline__ int4 ldg_keep(const int4* p)
-{
-#if B200MVS_PARAM_POLICY == 1
-    int4 v; asm("ld.global.nc.L1::evict_last.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p)); return v;
-#else
-    return __ldg(p);
-#endif
-}
 #endif
 
 // sRGB code value (byte K of `w`) -> linear, through the lane-replicated table in shared memory: entry v of replica r lives at

@@ -239,9 +239,9 @@ struct PatchT {
             const uint4* Lquad = nullptr;
             bool dok = false;
             {
-                const float4 wa = ldg_keep(reinterpret_cast<const float4*>(&V->w2c[0]));
-                const float4 wb = ldg_keep(reinterpret_cast<const float4*>(&V->w2c[4]));
-                const float4 wc = ldg_keep(reinterpret_cast<const float4*>(&V->w2c[8]));
+                const float4 wa = __ldg(reinterpret_cast<const float4*>(&V->w2c[0]));
+                const float4 wb = __ldg(reinterpret_cast<const float4*>(&V->w2c[4]));
+                const float4 wc = __ldg(reinterpret_cast<const float4*>(&V->w2c[8]));
                 A0x = wa.x * c0x + wa.y * c0y + wa.z * c0z + wa.w;
                 A0y = wb.x * c0x + wb.y * c0y + wb.z * c0z + wb.w;
                 A0z = wc.x * c0x + wc.y * c0y + wc.z * c0z + wc.w;
@@ -258,8 +258,8 @@ struct PatchT {
                     while (ratio < 0.5f) { ++l; ratio *= 2.f; }
                     const int nl = __ldg(&V->nlevels);
                     if (l > nl - 1) l = nl - 1;                     // clampLevel, minLevel = 0 (single_view.h:113-123)
-                    const float4 kk = ldg_keep(reinterpret_cast<const float4*>(&V->lv[l].ax));
-                    const int4 g = ldg_keep(reinterpret_cast<const int4*>(&V->lv[l].w));
+                    const float4 kk = __ldg(reinterpret_cast<const float4*>(&V->lv[l].ax));
+                    const int4 g = __ldg(reinterpret_cast<const int4*>(&V->lv[l].w));
                     Lax = kk.x; Lay = kk.y; Lcx = kk.z; Lcy = kk.w; wm1 = (float)(g.x - 1); hm1 = (float)(g.y - 1); Lpitch = g.z;
                     Lquad = reinterpret_cast<const uint4*>(__ldg(reinterpret_cast<const unsigned long long*>(&V->lv[l].quad)));
                     // projections of patchPoints[12] and patchPoints[12] + masterViewDirs[12]
@@ -336,7 +336,7 @@ struct PatchT {
                         const int left_ = (int)floorf(qx_), top_ = (int)floorf(qy_); \
                         nfx = qx_ - (float)left_; nfy = qy_ - (float)top_; \
                         noff = (unsigned)top_ * (unsigned)Lpitch + (unsigned)left_; \
-                        nQ = ldg_texel(Lquad + noff); \
+                        nQ = __ldg(Lquad + noff); \
                         nmt = *reinterpret_cast<const unsigned*>(mptr); \
                     } \
                 } while (0)
