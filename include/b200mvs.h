@@ -188,8 +188,11 @@ int b200mvs_set_patch_mode(b200mvs_ctx* ctx, int mode, int64_t thread_min);
  * the seed list of processFeatures (dmrecon.cc:179-292) - for the given reference views, so that a LATER
  * b200mvs_reconstruct of these views (same settings) starts its kernel at once.  May be called from another thread WHILE a
  * b200mvs_reconstruct of a previous batch is running (the reference overlaps them the same way: its OpenMP threads are in
- * different stages of different views, apps/dmrecon/dmrecon.cc:285); cameras and features must not change meanwhile.
- * A plan is used once and dropped; changing a camera or the features drops all plans. */
+ * different stages of different views, apps/dmrecon/dmrecon.cc:285); cameras and features must not change meanwhile
+ * (re-uploading the image of a view with an UNCHANGED camera is allowed).  b200mvs_global_view_selection of a planned view
+ * returns the plan's selection; b200mvs_reconstruct uses a plan once and drops it; changing a camera or the features drops
+ * all plans.  Host threads: up to hardware_concurrency(), or the value of the environment variable B200MVS_HOST_THREADS
+ * (several processes sharing one box, one per GPU). */
 int b200mvs_plan_views(b200mvs_ctx* ctx, const b200mvs_settings* s, int n_refs, const int32_t* ref_views);
 
 /* ---- batch of independent PatchOptimization runs: ctor + doAutoOptimization + computeConfidence
