@@ -78,3 +78,21 @@ def test_plan_views_runs_on_host_threads_without_a_gpu():
         g.plan_views(st, [99])
     with pytest.raises(dmrecon.B200MVSError):
         g.reconstruct(st, [0])            # planning context: no compute, no CPU fallback
+
+
+def test_planned_selection_is_what_global_view_selection_returns(monkeypatch):
+    """A prepared plan answers b200mvs_global_view_selection (the shim's leader asks for the selection of views its callers
+    planned on their own threads); the answer is the reference's selection whether it is computed or looked up, with one
+    planning thread (B200MVS_HOST_THREADS) or many, and a plan made under other settings is not used."""
+    from mve_b200 import dmrecon
+    s = golden_scene("T2")
+    ref = golden_ref("T2")
+    st = dmrecon.Settings(scale=s.scale, nr_recon_neighbors=s.nr_recon_neighbors, global_vs_max=20)
+    st3 = dmrecon.Settings(scale=s.scale, nr_recon_neighbors=s.nr_recon_neighbors, global_vs_max=3)
+    for threads in ("1", "3"):
+        monkeypatch.setenv("B200MVS_HOST_THREADS", threads)
+        g = _planning_scene(s)
+        g.plan_views(st, list(range(s.n_views)))
+        for v in range(s.n_views):
+            assert g.global_view_selection(st, v) == ref["gvs_default_%d" % v].tolist(), (threads, v)       # looked up
+            assert g.global_view_selection(st3, v) == ref["gvs_n3_%d" % v].tolist(), (threads, v)           # other settings: computed
