@@ -489,7 +489,7 @@ using PatchT1 = b200mvs::PatchT;   // one thread per patch (throughput: large ro
 // compiler it is spilled to local memory (~100 slots x 128 B per warp - more than L1 holds, so every reload in the per-view
 // set-up and tear-down was an L2 round trip: 19 % of the kernel's time in ncu's stall samples).  In shared memory a reload
 // costs a fixed ~30 cycles.
-constexpr size_t OPT_LUT_BYTES = sizeof(float) * (256 * LUT_REP);
+constexpr size_t OPT_LUT_BYTES = sizeof(float) * (256 * LUT_STRIDE);
 constexpr size_t OPT_SMEM_BYTES = OPT_LUT_BYTES + (size_t)OPT_TPB * sizeof(PatchT1);
 __device__ __forceinline__ PatchT1& thread_patch(float* smem)
 {
@@ -600,7 +600,7 @@ k_optimize(const Entry* __restrict__ in, PatchOut* __restrict__ out, int n, int 
            const float* __restrict__ g_lut, unsigned long long* counters)
 {
     extern __shared__ float smem[];
-    for (int i = threadIdx.x; i < 256 * LUT_REP; i += blockDim.x) smem[i] = g_lut[i / LUT_REP];
+    for (int i = threadIdx.x; i < 256 * LUT_STRIDE; i += blockDim.x) smem[i] = g_lut[i / LUT_STRIDE];
     __syncthreads();
     if (mode == 2 || (mode == 0 && n >= OPT_THREAD_MIN)) {
         PatchT1& p = thread_patch(smem);
@@ -783,7 +783,7 @@ __global__ void __launch_bounds__(OPT_TPB, OPT_MIN_BLOCKS)
 k_frontier(const FrontierParams P)
 {
     extern __shared__ float smem[];
-    for (int i = threadIdx.x; i < 256 * LUT_REP; i += blockDim.x) smem[i] = P.lut[i / LUT_REP];
+    for (int i = threadIdx.x; i < 256 * LUT_STRIDE; i += blockDim.x) smem[i] = P.lut[i / LUT_STRIDE];
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, gthreads = (size_t)gridDim.x * blockDim.x;

@@ -25,7 +25,8 @@ constexpr int MAX_LOCAL = 4;
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int NS = 25;
 constexpr int CENTER = 12;   // patch_sampler.cc:73,96
-constexpr int LUT_REP = 32;  // replicas of the sRGB table in shared memory (one per lane)
+constexpr int LUT_REP = 32;  // replicas of the sRGB table in shared memory that are used (one per lane)
+constexpr int LUT_STRIDE = 64; // floats per table value: a value's replicas start every 256 bytes (lut_k)
 
 struct alignas(16) LevelParams {   // ImagePyramidLevel (image_pyramid.h:28-59): K = [ax 0 cx; 0 ay cy; 0 0 1]
     float ax, ay, cx, cy;
@@ -84,12 +85,19 @@ __device__ __forceinline__ float rcp_fast(float x) { float r; asm("rcp.approx.ft
 __device__ __forceinline__ float rsqrt_fast(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 #endif
 
-// sRGB code value (byte K of `w`) -> linear, through the lane-replicated table in shared memory: entry v of replica r lives at
-// byte offset v * 128 + r * 4, so the offset is (byte << 7) | lane4 - one shift and one fused and-or (mvs_tools.cc:21-95).
+// sRGB code value (byte K of `w`) -> linear, through the lane-replicated table in shared memory (mvs_tools.cc:21-95).  Replica r of
+// value v lives at byte offset v * 256 + r * 4: with the values 256 bytes apart the offset is (byte << 8) | lane4, and that is
+// ONE instruction - a byte permute that drops byte K of the texel word next to the lane's own byte (lane4 < 128, the upper
+// bytes of that register are zero).  A stride of 128 bytes (no unused half) needs a shift and an and-or per look-up: 15
+// instructions more per sample.
 template <int K> __device__ __forceinline__ float lut_k(const float* table, unsigned lane4, unsigned w)
 {
-    static_assert(LUT_REP == 32, "offset arithmetic assumes 32 replicas");
-    const unsigned off = ((K == 0 ? (w << 7) : (w >> (8 * K - 7))) & 0x7F80u) | lane4;
+    static_assert(LUT_REP == 32 && LUT_STRIDE == 64, "offset arithmetic assumes 32 lanes and 256-byte rows");
+#if defined(B200MVS_HOST_EMU)
+    const unsigned off = (((w >> (8 * K)) & 0xFFu) << 8) | lane4;
+#else
+    const unsigned off = __byte_perm(w, lane4, 0x6504u | ((unsigned)K << 4));      // {lane4.b0, w.bK, 0, 0}
+#endif
     return *reinterpret_cast<const float*>(reinterpret_cast<const char*>(table) + off);
 }
 

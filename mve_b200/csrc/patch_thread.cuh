@@ -33,8 +33,10 @@ struct PatchT {
     // ---- constants of the thread ----
     const DevSettings* st;
     const ViewParams* views;
-    const float* lut_tab;      // lane-replicated srgb2lin table in shared memory (lut_k)
+#if defined(B200MVS_HOST_EMU)
+    const float* lut_tab;      // lane-replicated srgb2lin table (lut_k); on the device: table() / lane_offset()
     unsigned lane4;            // 4 * (lane of this thread)
+#endif
     // ---- constants of the patch ----
     const JobParams* job;
     unsigned xy;               // x | y << 16 of the patch centre
@@ -62,11 +64,11 @@ struct PatchT {
     // ---- per selected view (index = position in the ascending selected set) ----
     float cs[MAX_LOCAL][3];    // colorScale
     float ncc[MAX_LOCAL];      // NCC at the state of the last pass
-    // ---- results of the last pass ----
-    float p_num, p_den;
-    float nX0, nX1, nX2;
+    // (the sums a pass hands to the step that follows it - Gauss-Newton numerator / denominator, the solved normal
+    //  equations - are consumed in the same step() call: PassOut, a local of step())
 
 
+    struct PassOut { float num, den, nX0, nX1, nX2; };
     enum Stage { LVS_CTOR, CTOR, FIRST, PRE, POST, LVS_REPL, REPL, DONE };
     enum : unsigned {
         F_REF_OK = 1u << 0,        // sampler->success[refViewNr]
@@ -98,6 +100,14 @@ struct PatchT {
     // The table is the first thing in the kernels' dynamic shared memory (b200mvs.cu, OPT_SMEM_BYTES).  Read through the
     // member - the object itself lives in shared memory - the compiler would no longer know which address space it points
     // to and emit generic loads for the 15 look-ups of every sample.
+    __device__ __forceinline__ unsigned lane_offset() const
+    {
+#if defined(B200MVS_HOST_EMU)
+        return lane4;
+#else
+        return (threadIdx.x & 31u) << 2;
+#endif
+    }
     __device__ __forceinline__ const float* table() const
     {
 #if defined(B200MVS_HOST_EMU)
@@ -140,7 +150,7 @@ struct PatchT {
     __device__ __forceinline__ void init_sampler(int x, int y)
     {
         const float* const lut_tab = table();
-        const unsigned lane4 = this->lane4;
+        const unsigned lane4 = lane_offset();
         pk &= ~F_REF_OK; mm = 0.f; inv_mm = 0.f; sqrDevX = 0.f;
         mx0 = mx1 = mx2 = 0.f;
         crx = cry = crz = cpx = cpy = cpz = mfp = inv_mfp = 0.f;
@@ -200,12 +210,12 @@ struct PatchT {
 
     // One pass at the current state (same contract as PatchW::pass).
     // `cand`: NCC per candidate global slot, written by a candidates pass for the lvs_greedy() that follows it.
-    __device__ __forceinline__ void pass(bool candidates, bool cs_pending, bool want_ncc, bool want_normal, float* cand)
+    __device__ __forceinline__ void pass(bool candidates, bool cs_pending, bool want_ncc, bool want_normal, float* cand, PassOut& po)
     {
         // The object lives in shared memory (k_frontier): what the sample loop reads 25 times per sweep is copied into
         // registers here, everything else is read where it is needed.
         const float* const lut_tab = table();
-        const unsigned lane4 = this->lane4;
+        const unsigned lane4 = lane_offset();
         const float u0x = this->u0x, u0y = this->u0y, u0z = this->u0z, uax = this->uax, uay = this->uay, uaz = this->uaz;
         const float ubx = this->ubx, uby = this->uby, ubz = this->ubz;
         const float depth = this->depth, dzI = this->dzI, dzJ = this->dzJ;
@@ -467,7 +477,7 @@ struct PatchT {
             }
         }
         if (candidates) return;
-        p_num = num; p_den = den;
+        po.num = num; po.den = den;
         put(F_HAS_NORMAL, want_normal);
         put(F_HAS_NCC, want_ncc);
         if (want_normal) {
@@ -488,20 +498,20 @@ struct PatchT {
             inv[8] = m[0] * m[4] - m[1] * m[3];
 #pragma unroll
             for (int q = 0; q < 9; ++q) inv[q] /= det;
-            nX0 = (float)(inv[0] * E0 + inv[1] * E1 + inv[2] * E2);
-            nX1 = (float)(inv[3] * E0 + inv[4] * E1 + inv[5] * E2);
-            nX2 = (float)(inv[6] * E0 + inv[7] * E1 + inv[8] * E2);
+            po.nX0 = (float)(inv[0] * E0 + inv[1] * E1 + inv[2] * E2);
+            po.nX1 = (float)(inv[3] * E0 + inv[4] * E1 + inv[5] * E2);
+            po.nX2 = (float)(inv[6] * E0 + inv[7] * E1 + inv[8] * E2);
         }
     }
 
     __device__ __forceinline__ bool all_der_ok() const { return ((pk >> SH_DER) & 0xFu) == ((1u << nsel()) - 1u); }
 
     // optimizeDepthOnly (patch_optimization.cc:265-299) from the sums of the last pass. Returns true when the state moved.
-    __device__ __forceinline__ bool depth_step()
+    __device__ __forceinline__ bool depth_step(const PassOut& po)
     {
         if (!all_der_ok()) { pk &= ~F_OPTI; return false; }
-        if (p_den > 0.f) {
-            depth += p_num / p_den;
+        if (po.den > 0.f) {
+            depth += po.num / po.den;
             update();
             put(F_OPTI, is(F_REF_OK));
             return true;
@@ -510,11 +520,11 @@ struct PatchT {
     }
 
     // optimizeDepthAndNormal (patch_optimization.cc:302-364) from the solution prepared by the last pass.
-    __device__ __forceinline__ bool normal_step()
+    __device__ __forceinline__ bool normal_step(const PassOut& po)
     {
         if (!all_der_ok()) { pk &= ~F_OPTI; return false; }
         if (is(F_SINGULAR)) { pk &= ~F_OPTI; return false; }
-        dzI += nX1; dzJ += nX2; depth += nX0;
+        dzI += po.nX1; dzJ += po.nX2; depth += po.nX0;
         update();
         put(F_OPTI, is(F_REF_OK));
         return true;
@@ -631,8 +641,6 @@ struct PatchT {
         iter = 0;
         pk = F_OPTI | F_SINGULAR | ((unsigned)DONE << SH_STAGE);      // opti = true, n_singular = true, everything else clear
         avail = 0u;
-        p_num = p_den = 0.f;
-        nX0 = nX1 = nX2 = 0.f;
         u0x = u0y = u0z = uax = uay = uaz = ubx = uby = ubz = c0x = c0y = c0z = 0.f;
         init_sampler(in.x, in.y);
         selp = in.slots;                                 // propagated ids arrive ascending, 0xFF padded
@@ -671,7 +679,8 @@ struct PatchT {
         const bool a_normal = (stage == REPL) | ((stage == FIRST) & (iter == 4)) | ((stage == PRE) & is(F_NORMAL)) |
                               ((stage == POST) & ((iter + 1) % 5 == 4));
         float cand[MAX_GLOBAL];      // candidates' NCCs: local memory, touched on the (rare) view-selection passes only
-        pass(a_cand, a_cs, a_ncc, a_normal, cand);
+        PassOut po = {0.f, 0.f, 0.f, 0.f, 0.f};
+        pass(a_cand, a_cs, a_ncc, a_normal, cand, po);
         if (stage == LVS_CTOR || stage == LVS_REPL) {
             lvs_greedy(cand);
             if (!is(F_LVS_OK)) { if (stage == LVS_CTOR) pk &= ~F_OPTI; set_stage(DONE); return true; }
@@ -700,7 +709,7 @@ struct PatchT {
             ++iter;
         }
         while (iter < 4 && is(F_OPTI)) {
-            const bool moved = depth_step();
+            const bool moved = depth_step(po);
             ++iter;
             if (moved && is(F_OPTI)) { set_stage(FIRST); return false; }
         }
@@ -711,8 +720,8 @@ struct PatchT {
         if (!is(F_HAS_NCC) || (normal && !is(F_HAS_NORMAL))) { set_stage(PRE); return false; }
         // (oldNCC = ncc here in the reference: the comparison is taken when the next pass overwrites the NCC)
         pk &= ~F_OPTI;
-        if (normal) { normal_step(); pk &= ~F_VIEW_REMOVED; pk |= F_WAS_NORMAL; }
-        else { depth_step(); pk &= ~F_WAS_NORMAL; }
+        if (normal) { normal_step(po); pk &= ~F_VIEW_REMOVED; pk |= F_WAS_NORMAL; }
+        else { depth_step(po); pk &= ~F_WAS_NORMAL; }
         if (!is(F_OPTI)) { set_stage(DONE); return true; }
         set_stage(POST);
         return false;
@@ -758,13 +767,17 @@ struct PatchT {
 // PatchT objects sit side by side in shared memory (k_frontier).  With 8-byte members the stride cannot be an odd number of
 // words; 2 mod 4 words keeps the conflicts of a warp's accesses to one member at 2-way (these are the once-per-sweep
 // accesses, not the table look-ups of the sample loop).
-static_assert(sizeof(PatchT) % 16 == 8, "PatchT stride in shared memory must be 8 mod 16 bytes");
+static_assert(sizeof(PatchT) % 16 == 8 && sizeof(PatchT) <= 248, "PatchT stride in shared memory must be 8 mod 16 bytes, and 512 of them must fit beside the table");
 #endif
 
 __device__ __forceinline__ void bind_thread(PatchT& p, const DevSettings* st, const ViewParams* views, const float* lut_rep, int tid)
 {
     p.st = st; p.views = views;
+#if defined(B200MVS_HOST_EMU)
     p.lut_tab = lut_rep; p.lane4 = 4u * (unsigned)(tid & (LUT_REP - 1));
+#else
+    (void)lut_rep; (void)tid;      // the table is the start of the dynamic shared memory, the lane comes from threadIdx
+#endif
     p.pk = (unsigned)PatchT::DONE << PatchT::SH_STAGE;
     p.n_sets = 0u;
 }

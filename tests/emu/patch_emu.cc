@@ -77,8 +77,8 @@ int emu_optimize_patches(const EmuView* views, int n_views, int ref_view, int W,
 
     if (mode == 2) {
         /* one THREAD per patch (patch_thread.cuh): no collectives, so the device code simply runs patch after patch */
-        std::vector<float> lut_rep(256 * LUT_REP);
-        for (int i = 0; i < 256 * LUT_REP; ++i) lut_rep[i] = lut[i / LUT_REP];
+        std::vector<float> lut_rep(256 * LUT_STRIDE);
+        for (int i = 0; i < 256 * LUT_STRIDE; ++i) lut_rep[i] = lut[i / LUT_STRIDE];
         PatchT p;
         bind_thread(p, &st, vp.data(), lut_rep.data(), 0);
         for (int i = 0; i < n; ++i) {
@@ -98,8 +98,8 @@ int emu_optimize_patches(const EmuView* views, int n_views, int ref_view, int W,
     /* one warp per patch (patch_warp.cuh): 32 host threads run the device code lane by lane; "shared memory" = the
      * replicated table */
     simt_emu::Warp warp;
-    std::vector<float> lut_rep(256 * LUT_REP);
-    for (int i = 0; i < 256 * LUT_REP; ++i) lut_rep[i] = lut[i / LUT_REP];
+    std::vector<float> lut_rep(256 * LUT_STRIDE);
+    for (int i = 0; i < 256 * LUT_STRIDE; ++i) lut_rep[i] = lut[i / LUT_STRIDE];
     std::vector<std::thread> lanes;
     for (int lane = 0; lane < 32; ++lane) {
         lanes.emplace_back([&, lane]() {
