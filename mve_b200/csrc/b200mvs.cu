@@ -476,10 +476,10 @@ __global__ void k_export_rgb(const uchar4* __restrict__ src, int w, int h, int p
 // kernels: patch optimisation + frontier
 // ------------------------------------------------------------------------------------------------
 #ifndef OPT_TPB
-#define OPT_TPB 512          // threads per CTA of the patch-optimisation kernels: one CTA per SM shares ONE 32 KB table (more L1 left)
+#define OPT_TPB 512          // threads per CTA of the patch-optimisation kernels: one CTA per SM shares ONE 64 KB table
 #endif
 #ifndef OPT_MIN_BLOCKS
-#define OPT_MIN_BLOCKS 1     // CTAs per SM: registers per thread <= 65536 / (OPT_MIN_BLOCKS * OPT_TPB) = 128; shared memory 32 KB per CTA
+#define OPT_MIN_BLOCKS 1     // CTAs per SM: registers per thread <= 65536 / (OPT_MIN_BLOCKS * OPT_TPB) = 128; shared memory 180 KB per CTA
 #endif
 constexpr int OPT_WARPS = OPT_TPB / 32;
 using PatchT = b200mvs::PatchW;    // one warp per patch (latency: small rounds)
