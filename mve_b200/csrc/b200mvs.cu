@@ -145,7 +145,7 @@ struct b200mvs_ctx {
     int frontier_grid = 0;             // CTAs of the cooperative launch (= what fits on the chip)
     int optimize_grid = 0;             // resident CTAs of k_optimize
     long long thread_min = -1;         // reconstruct: rounds with at least this many patches run one thread per patch (-1: default)
-    int optimize_mode = 0;             // b200mvs_optimize_patches: 0 by batch size, 1 eight lanes per patch, 2 one thread per patch
+    int optimize_mode = 0;             // b200mvs_optimize_patches: 0 by batch size, 1 one warp per patch, 2 one thread per patch
     unsigned long long* h_counters = nullptr;   // pinned
     unsigned long long* h_mirror = nullptr;     // pinned + mapped: HostMirror
     std::vector<cudaEvent_t> ev_pool;
