@@ -1,6 +1,6 @@
 """Agreement of the per-pixel local view sets (runs on the GPU box):
 
-    python tools/parity_view_ids.py C2 5 [out.json]
+    python tests/measure_view_ids.py C2 5 [out.json]
 
 The reference CLI does not save which 4 neighbour views a pixel was reconstructed from, so the map-level agreement of the
 local view ids is measured against the oracle's strict-priority-order run (oracle/mvs_oracle.cc, pinned against the
@@ -13,7 +13,7 @@ import time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 from mve_b200 import dmrecon, synth          # noqa: E402
-from oracle import oracle_py                 # noqa: E402  (test infrastructure: this is a measurement tool, not the product)
+from oracle import oracle_py                 # noqa: E402  (test infrastructure: a measurement script under tests/: the oracle is test infrastructure)
 from tests.util import map_parity            # noqa: E402
 
 
